@@ -137,6 +137,18 @@ int sphb200_step(sphb200_sim *sim, int64_t n_steps, int reset_delta_x, sphb200_r
 int sphb200_get_report(sphb200_sim *sim, sphb200_report *report);
 /* number of this library's kernel launches since create (bench.py's gpu_launches) */
 int64_t sphb200_launch_count(const sphb200_sim *sim);
+/* run all of this handle's work on the caller's CUDA stream (a cudaStream_t; NULL = the legacy
+ * default stream) instead of the handle's own, so that the caller's CUDA events bracket it */
+int sphb200_set_stream(sphb200_sim *sim, void *cuda_stream);
+/* tuning knobs: "compact" (0/1 two-phase neighbour lists), "tma" (0/1 cp.async.bulk staging),
+ * "smem_kb" (shared memory per CTA of the interaction kernel), "batch" (steps per host sync),
+ * "generic" (1 = force the run-time-dispatched pair body) */
+int sphb200_set_option(sphb200_sim *sim, const char *name, double value);
+/* device time (ms) of the stages of ONE extra step, the analogue of the reference's TimerOutputs
+ * sections (src/SPHCellList.jl:748-800): [0] Δt/Δx reductions + control ("01"), [1] neighbour
+ * rebuild + motion + mDBC ("02"-"04"), [2] first NeighborLoop + half step ("05"-"07"),
+ * [3] second NeighborLoop + full step ("08"-"11"), [4] metadata ("12").  Advances the simulation. */
+int sphb200_stage_times(sphb200_sim *sim, double *ms_out, int n);
 
 /* ---- stage-level entry points (the reference's exported step functions) ------------- */
 /* UpdateNeighbors!(Particles, H⁻¹, …), src/SPHCellList.jl:138-163: hash → stable sort by cell

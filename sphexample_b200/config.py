@@ -245,6 +245,8 @@ def next_output_time(meta: SimulationMetaData) -> float:
     if isinstance(times, (int, float)):
         return times * meta.OutputIterationCounter
     idx = meta.OutputIterationCounter  # Julia is 1-based: times[idx]
+    if idx < 1:
+        return 0.0  # (the reference indexes times[0] here, out of bounds under @inbounds)
     if idx < len(times):
         return times[idx - 1]
     return meta.SimulationTime

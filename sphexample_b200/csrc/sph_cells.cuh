@@ -1,0 +1,355 @@
+// sph_cells.cuh — UpdateNeighbors! on the device (src/SPHCellList.jl:56-61,118-163):
+// particle -> cell hash, stable counting-sort reorder, dense cell start table, brick list.
+//
+// All kernels are predicated on ctl->do_rebuild so that the whole step sequence can be
+// enqueued (or graph-captured) without the host knowing whether this step rebuilds.
+//
+// The reference sorts the particle table by CartesianIndex (last dimension most significant,
+// x fastest) with a stable sort.  Here the key is
+//     key = ((c_s - cmin_s) * nm + (c_m - cmin_m)) * nx + (c_x - cmin_x)
+// on a dense grid over the bounding box of occupied cells padded by one cell on every side
+// (so the 3^D stencil never leaves the table).  s is the slab axis (most significant so that
+// slab halos are contiguous index ranges); with s = last dimension this is exactly the
+// reference's ordering.  Stability: an atomic counting sort places particles of one cell in
+// arbitrary order, then k_stable_rank re-ranks each cell's members by their previous index,
+// which is what a stable sort would have produced — deterministic run to run.
+#pragma once
+
+#include "sph_device.cuh"
+
+namespace sph {
+
+struct AxisMap {
+    int ax_m, ax_s;   // which position component is the m / s axis (x is always component 0)
+};
+
+// map_floor, src/SPHCellList.jl:56-61: sign(x) * trunc(muladd(|x|, H⁻¹, 0.5)), evaluated in
+// double for both storage precisions so that an fp32 run bins exactly like the fp64 oracle fed
+// the same (fp32-representable) positions.
+__device__ __forceinline__ int map_floor_dev(double x, double inv_cutoff, int &bad) {
+    double t = trunc(fma(fabs(x), inv_cutoff, 0.5));
+    if (!(t < 1.0e9)) {   // also catches NaN
+        bad = 1;
+        t = 0.0;
+    }
+    int s = (x > 0.0) - (x < 0.0);
+    return s * (int)t;
+}
+
+template <class T, int D>
+__global__ void k_cell_bbox(const typename Lay<T, D>::TA *__restrict__ A, int n, double inv_cutoff,
+                            int *__restrict__ ccoord, Ctl *ctl, GridInfo *grid) {
+    if (ctl->error || ctl->done || !ctl->do_rebuild) return;
+    int lo[D], hi[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        lo[k] = INT_MAX;
+        hi[k] = INT_MIN;
+    }
+    int bad = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        T x[D];
+        Lay<T, D>::pos(A[i], x);
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            int c = map_floor_dev((double)x[k], inv_cutoff, bad);
+            ccoord[(size_t)i * D + k] = c;
+            lo[k] = min(lo[k], c);
+            hi[k] = max(hi[k], c);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        lo[k] = warp_min(lo[k]);
+        hi[k] = warp_max(hi[k]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            if (lo[k] <= hi[k]) {
+                atomicMin(&grid->bb_min[k], lo[k]);
+                atomicMax(&grid->bb_max[k], hi[k]);
+            }
+        }
+    }
+    if (bad) atomicCAS(&ctl->error, 0, SPH_ERR_ENUMERIC);
+}
+
+// One thread: dense grid extents from the bounding box.  own_lo/own_hi: owned cell-coordinate
+// range [lo, hi) along the slab axis (INT_MIN/INT_MAX when not decomposed).
+template <int D>
+__global__ void k_grid_setup(Ctl *ctl, GridInfo *grid, AxisMap am, long long cell_cap, long long row_cap,
+                             int own_lo, int own_hi) {
+    if (ctl->error || ctl->done || !ctl->do_rebuild) return;
+    int ext[3] = {1, 1, 1};
+    for (int k = 0; k < D; ++k) {
+        long long e = (long long)grid->bb_max[k] - (long long)grid->bb_min[k] + 3;
+        if (e < 3 || e > (1ll << 30)) {
+            ctl->error = SPH_ERR_ECAPACITY;
+            return;
+        }
+        ext[k] = (int)e;
+        grid->cmin[k] = grid->bb_min[k] - 1;
+    }
+    int nx = ext[0];
+    int nm = (D == 3) ? ext[am.ax_m] : 1;
+    int ns = ext[am.ax_s];
+    long long ncell = (long long)nx * nm * ns;
+    long long nrows = (long long)nm * ns;
+    if (ncell + 1 > cell_cap || nrows > row_cap) {
+        ctl->error = SPH_ERR_ECAPACITY;
+        return;
+    }
+    grid->nx = nx;
+    grid->nm = nm;
+    grid->ns = ns;
+    grid->ncell = (int)ncell;
+    grid->nrows = (int)nrows;
+    // owned rows: slab coordinate c_s in [own_lo, own_hi)
+    long long s0 = (long long)own_lo - grid->cmin[am.ax_s];
+    long long s1 = (long long)own_hi - grid->cmin[am.ax_s];
+    if (own_lo == INT_MIN) s0 = 0;
+    if (own_hi == INT_MAX) s1 = ns;
+    s0 = s0 < 0 ? 0 : (s0 > ns ? ns : s0);
+    s1 = s1 < s0 ? s0 : (s1 > ns ? ns : s1);
+    grid->own_row0 = (int)(s0 * nm);
+    grid->own_row1 = (int)(s1 * nm);
+}
+
+__global__ void k_zero_counts(const Ctl *ctl, const GridInfo *grid, int *__restrict__ cell_count) {
+    if (ctl->error || ctl->done || !ctl->do_rebuild) return;
+    int n = grid->ncell + 1;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) cell_count[c] = 0;
+}
+
+template <int D>
+__global__ void k_cell_count(const int *__restrict__ ccoord, int n, AxisMap am, const Ctl *ctl,
+                             const GridInfo *grid, int *__restrict__ key_out, int *__restrict__ slot_out,
+                             int *__restrict__ cell_count) {
+    if (ctl->error || ctl->done || !ctl->do_rebuild) return;
+    const int nx = grid->nx, nm = grid->nm;
+    const int cx0 = grid->cmin[0], cm0 = (D == 3) ? grid->cmin[am.ax_m] : 0, cs0 = grid->cmin[am.ax_s];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int cx = ccoord[(size_t)i * D + 0] - cx0;
+        int cm = (D == 3) ? ccoord[(size_t)i * D + am.ax_m] - cm0 : 0;
+        int cs = ccoord[(size_t)i * D + am.ax_s] - cs0;
+        int key = (cs * nm + cm) * nx + cx;
+        key_out[i] = key;
+        slot_out[i] = atomicAdd(&cell_count[key], 1);
+    }
+}
+
+// ---- exclusive scan of cell_count[0 .. ncell] into cell_start (three small kernels) ----------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *smem_warp, int &total) {
+    // inclusive warp scan
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) smem_warp[w] = inc;
+    __syncthreads();
+    int nw = blockDim.x >> 5;
+    if (w == 0) {
+        int s = lane < nw ? smem_warp[lane] : 0;
+        int si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= o) si += u;
+        }
+        if (lane < nw) smem_warp[lane] = si - s;   // exclusive warp offsets
+        if (lane == 31) smem_warp[32] = si;        // block total
+    }
+    __syncthreads();
+    int res = smem_warp[w] + inc - v;
+    total = smem_warp[32];
+    __syncthreads();
+    return res;
+}
+
+__global__ void k_scan_partials(const Ctl *ctl, const GridInfo *grid, const int *__restrict__ cell_count,
+                                int *__restrict__ partial) {
+    if (ctl->error || ctl->done || !ctl->do_rebuild) return;
+    __shared__ int sw[33];
+    int n = grid->ncell + 1;
+    int base = blockIdx.x * SCAN_CHUNK;
+    if (base >= n) return;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        int c = base + k * SCAN_THREADS + threadIdx.x;
+        if (c < n) s += cell_count[c];
+    }
+    int total;
+    block_exclusive_scan(s, sw, total);
+    if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+
+__global__ void k_scan_top(const Ctl *ctl, const GridInfo *grid, int *__restrict__ partial) {
+    if (ctl->error || ctl->done || !ctl->do_rebuild) return;
+    __shared__ int sw[33];
+    int n = grid->ncell + 1;
+    int nblk = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    int carry = 0;
+    for (int b0 = 0; b0 < nblk; b0 += blockDim.x) {
+        int b = b0 + threadIdx.x;
+        int v = b < nblk ? partial[b] : 0;
+        int total;
+        int ex = block_exclusive_scan(v, sw, total);
+        if (b < nblk) partial[b] = carry + ex;
+        carry += total;
+    }
+}
+
+__global__ void k_scan_final(const Ctl *ctl, const GridInfo *grid, const int *__restrict__ cell_count,
+                             const int *__restrict__ partial, int *__restrict__ cell_start) {
+    if (ctl->error || ctl->done || !ctl->do_rebuild) return;
+    __shared__ int sw[33];
+    int n = grid->ncell + 1;
+    int base = blockIdx.x * SCAN_CHUNK;
+    if (base >= n) return;
+    // thread t owns SCAN_ITEMS consecutive cells
+    int c0 = base + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (c0 + k < n) ? cell_count[c0 + k] : 0;
+        s += v[k];
+    }
+    int total;
+    int ex = block_exclusive_scan(s, sw, total) + partial[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (c0 + k < n) cell_start[c0 + k] = ex;
+        ex += v[k];
+    }
+}
+
+__global__ void k_scatter_unstable(const Ctl *ctl, const int *__restrict__ key, const int *__restrict__ slot, int n,
+                                   const int *__restrict__ cell_start, int *__restrict__ tmp_idx) {
+    if (ctl->error || ctl->done || !ctl->do_rebuild) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        tmp_idx[cell_start[key[i]] + slot[i]] = i;
+}
+
+// stable order inside each cell = ascending previous index
+__global__ void k_stable_rank(const Ctl *ctl, const int *__restrict__ key, const int *__restrict__ tmp_idx, int n,
+                              const int *__restrict__ cell_start, int *__restrict__ perm) {
+    if (ctl->error || ctl->done || !ctl->do_rebuild) return;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        int v = tmp_idx[p];
+        int c = key[v];
+        int s = cell_start[c], e = cell_start[c + 1];
+        int rank = 0;
+        for (int q = s; q < e; ++q) rank += (tmp_idx[q] < v);
+        perm[s + rank] = v;
+    }
+}
+
+// gather the particle table into scratch (new order), then copy back
+template <class T, int D>
+struct Table {
+    typename Lay<T, D>::TA *A;
+    typename Lay<T, D>::TB *B;
+    typename Lay<T, D>::TV *acc;
+    typename Lay<T, D>::TV *ghost;   // may be null
+    long long *id;
+    unsigned long long *group;
+    uint8_t *type;
+    int *ckey;
+};
+
+template <class T, int D>
+__global__ void k_gather_table(const Ctl *ctl, const int *__restrict__ perm, int n, Table<T, D> src, Table<T, D> dst,
+                               const int *__restrict__ key_prev_order) {
+    if (ctl->error || ctl->done || !ctl->do_rebuild) return;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        int s = perm[p];
+        dst.A[p] = src.A[s];
+        dst.B[p] = src.B[s];
+        dst.acc[p] = src.acc[s];
+        if (src.ghost) dst.ghost[p] = src.ghost[s];
+        dst.id[p] = src.id[s];
+        dst.group[p] = src.group[s];
+        dst.type[p] = src.type[s];
+        dst.ckey[p] = key_prev_order[s];
+    }
+}
+
+template <class T, int D>
+__global__ void k_copy_table(const Ctl *ctl, int n, Table<T, D> src, Table<T, D> dst) {
+    if (ctl->error || ctl->done || !ctl->do_rebuild) return;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        dst.A[p] = src.A[p];
+        dst.B[p] = src.B[p];
+        dst.acc[p] = src.acc[p];
+        if (src.ghost) dst.ghost[p] = src.ghost[p];
+        dst.id[p] = src.id[p];
+        dst.group[p] = src.group[p];
+        dst.type[p] = src.type[p];
+        dst.ckey[p] = src.ckey[p];
+    }
+}
+
+// Brick list: every owned row (c_m, c_s) of cells is cut into segments of at most `bt`
+// consecutive particles; one brick is the unit of work of the interaction kernel.
+__global__ void k_build_bricks(Ctl *ctl, GridInfo *grid, const int *__restrict__ cell_start, int bt,
+                               Brick *__restrict__ bricks, int brick_cap, int n) {
+    if (ctl->error || ctl->done || !ctl->do_rebuild) return;
+    __shared__ int sw[33];
+    __shared__ int s_carry;
+    const int nx = grid->nx;
+    const int r0 = grid->own_row0, r1 = grid->own_row1;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int rb = r0; rb < r1; rb += blockDim.x) {
+        int r = rb + threadIdx.x;
+        int p0 = 0, p1 = 0;
+        if (r < r1) {
+            p0 = cell_start[(size_t)r * nx];
+            p1 = cell_start[(size_t)(r + 1) * nx];
+        }
+        int nb = (p1 - p0 + bt - 1) / bt;
+        int total;
+        int off = block_exclusive_scan(nb, sw, total) + s_carry;
+        for (int k = 0; k < nb; ++k) {
+            if (off + k < brick_cap) {
+                Brick b;
+                b.t0 = p0 + k * bt;
+                b.t1 = min(p0 + (k + 1) * bt, p1);
+                bricks[off + k] = b;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (s_carry > brick_cap) {
+            ctl->error = SPH_ERR_ECAPACITY;
+            grid->nbricks = 0;
+        } else {
+            grid->nbricks = s_carry;
+        }
+        grid->own_p0 = cell_start[(size_t)r0 * nx];
+        grid->own_p1 = cell_start[(size_t)r1 * nx];
+        grid->n_total = n;
+        ctl->n_rebuilds += 1;
+    }
+}
+
+// last kernel of the rebuild sequence: a successful rebuild clears the request
+__global__ void k_finish_rebuild(Ctl *ctl) {
+    if (ctl->error || ctl->done) return;
+    ctl->do_rebuild = 0;
+}
+
+}  // namespace sph

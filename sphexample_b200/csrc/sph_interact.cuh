@@ -1,0 +1,403 @@
+// sph_interact.cuh — the fused neighbour-traversal kernel: NeighborLoop! ∘ ComputeInteractions!
+// (src/SPHCellList.jl:168-217,268-317) as a GATHER over the full 3^D stencil, with the
+// symplectic half/full updates (src/SPHCellList.jl:624-677) fused into its epilogue.
+//
+// Work unit = one "brick": up to BT consecutive (cell-sorted) particles of one row of cells.
+// Because x is the fastest key component, the candidates of a brick are, for each of the
+// 3^(D-1) neighbouring rows, ONE contiguous span of the sorted arrays (cells cx0-1 .. cx1+1):
+//   * one elected thread stages those 9 (3 in 2D) spans of each packed array into shared memory
+//     with cp.async.bulk (1-D TMA) completing on an mbarrier;
+//   * each thread owns one target particle; a warp walks the union of its lanes' windows with
+//     broadcast shared-memory reads and tests the cut-off (phase 1, cheap, ~18 % hit rate in 3D);
+//   * accepted neighbours are appended to a per-thread list in shared memory and the ~70-flop
+//     pair body runs afterwards over the lists (phase 2), so the expensive body executes on
+//     densely populated warps instead of under an 18 %-full predicate mask;
+//   * no atomics, no per-thread accumulator copies (ResetStep!/ReductionStep!, :367-484, vanish).
+// Persistent CTAs fetch bricks from an atomic work counter.
+//
+// Pair-set fidelity: a candidate b is evaluated for target a iff b's (stale) cell is within the
+// 3^D stencil of a's (stale) cell AND |x_a - x_b|² <= H² now — exactly the reference's set,
+// including its misses between rebuilds — hence the per-lane window test.
+#pragma once
+
+#include "sph_device.cuh"
+
+namespace sph {
+
+constexpr int LIST_CAP = 64;        // per-thread accepted-neighbour list entries
+constexpr int ROLE_BIT = 0x8000;
+
+enum { EPI_STORE = 0, EPI_FUSED = 1 };
+
+template <class T, int D>
+struct InteractArgs {
+    using L = Lay<T, D>;
+    // pass inputs: state n (pass 0) or state n+½ (pass 1)
+    const typename L::TA *A;
+    const typename L::TB *B;
+    const T *RN;                       // ρₙ (pass 1: state-n density, Q2); unused in pass 0
+    const typename L::TB *Bn;          // vₙ of neighbours (pass 1 + LaminarSPS only)
+    // own state n, read and overwritten by the fused corrector (pass 1)
+    typename L::TA *An_rw;
+    typename L::TB *Bn_rw;
+    // fused predictor output (pass 0)
+    typename L::TA *Ah_out;
+    typename L::TB *Bh_out;
+    // plain outputs
+    T *drhodt;                         // EPI_STORE
+    typename L::TV *acc;               // EPI_STORE and fused corrector
+    typename L::TV *gradC;             // PlanarShifting
+    T *divr;
+    T *ksum;                           // StoreKernelOutput
+    typename L::TV *kgrad;
+    // cell list
+    const int *cell_start;
+    const int *ckey;
+    const uint8_t *type;
+    const Brick *bricks;
+    const GridInfo *grid;
+    Ctl *ctl;
+    Phys<T> phys;
+    int cap;                           // staged candidates per stage (multiple of 4)
+    int epilogue;                      // EPI_STORE / EPI_FUSED
+    int use_tma;                       // 1: cp.async.bulk staging, 0: cooperative ld/st staging
+    int ref_major_is_s;                // 1: slab axis is the reference's most significant axis
+    int counter_slot;                  // which ctl->work_counter this launch consumes
+};
+
+template <class T, int D, int PASS, bool GENERIC>
+struct StageSizes {
+    using L = Lay<T, D>;
+    static constexpr int esA = sizeof(typename L::TA);
+    static constexpr int esB = sizeof(typename L::TB);
+    static constexpr int esR = PASS ? sizeof(T) : 0;
+    static constexpr int esBn = (PASS && GENERIC) ? sizeof(typename L::TB) : 0;
+    static constexpr int per_candidate = esA + esB + esR + esBn;
+};
+
+template <class T, int D, int PASS, bool GENERIC, bool COMPACT, int BT>
+__global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
+    using L = Lay<T, D>;
+    using TA = typename L::TA;
+    using TB = typename L::TB;
+    using TV = typename L::TV;
+    constexpr int NR = (D == 3) ? 9 : 3;
+    using SS = StageSizes<T, D, PASS, GENERIC>;
+
+    if (g.ctl->error || g.ctl->done) return;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int cap = g.cap;
+    TA *sA = reinterpret_cast<TA *>(smem_raw);
+    TB *sB = reinterpret_cast<TB *>(smem_raw + (size_t)cap * SS::esA);
+    T *sR = reinterpret_cast<T *>(smem_raw + (size_t)cap * (SS::esA + SS::esB));
+    TB *sBn = reinterpret_cast<TB *>(smem_raw + (size_t)cap * (SS::esA + SS::esB + SS::esR));
+    unsigned short *slist = reinterpret_cast<unsigned short *>(smem_raw + (size_t)cap * SS::per_candidate);
+    // (slist is LIST_CAP * BT entries when COMPACT, otherwise unused / zero-sized)
+
+    __shared__ uint64_t s_bar;
+    __shared__ int s_brick;
+    __shared__ int s_w0a[NR], s_len[NR], s_off[NR + 1];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const Phys<T> &ph = g.phys;
+    const bool use_sps = GENERIC && PASS && (ph.viscosity == V_SPS);
+
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+
+    const int nx = g.grid->nx, nm = g.grid->nm;
+    const int nbricks = g.grid->nbricks;
+    const int npad = (g.grid->n_total + 3) & ~3;
+
+    for (;;) {
+        if (tid == 0) s_brick = atomicAdd(&g.ctl->work_counter[g.counter_slot], 1);
+        __syncthreads();
+        const int bidx = s_brick;
+        if (bidx >= nbricks) break;
+        const Brick br = g.bricks[bidx];
+        const int key0 = g.ckey[br.t0], key1 = g.ckey[br.t1 - 1];
+        const int cx0 = key0 % nx, cx1 = key1 % nx;
+        const int rowbase = key0 - cx0;
+
+        // ---- candidate spans of the 3^(D-1) neighbouring rows (aligned to 4 elements) ----
+        if (tid < NR) {
+            int dm = (D == 3) ? (tid % 3 - 1) : 0;
+            int ds = (D == 3) ? (tid / 3 - 1) : (tid - 1);
+            int rk = rowbase + (ds * nm + dm) * nx;
+            int w0 = g.cell_start[rk + cx0 - 1];
+            int w1 = g.cell_start[rk + cx1 + 2];
+            int w0a = w0 & ~3;
+            int w1a = min((w1 + 3) & ~3, npad);
+            if (w1 <= w0) w1a = w0a;   // empty row: stage nothing
+            s_w0a[tid] = w0a;
+            s_len[tid] = w1a - w0a;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int o = 0;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                s_off[r] = o;
+                o += s_len[r];
+            }
+            s_off[NR] = o;
+        }
+        __syncthreads();
+        const int total = s_off[NR];
+
+        // ---- this thread's target particle ------------------------------------------------
+        const int i = br.t0 + tid;
+        const bool valid = i < br.t1;
+        T xa[D], va[D], rho_a = T(1), P_a = T(0), rhon_a = T(1), ml_a = T(0);
+        int cxi = cx0, cs_a = 0, ce_a = 0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) xa[k] = va[k] = T(0);
+        if (valid) {
+            T rs;
+            L::unpack(g.A[i], g.B[i], xa, va, rs, P_a);
+            rho_a = sph_abs(rs);
+            ml_a = rs > T(0) ? T(1) : T(0);
+            rhon_a = PASS ? g.RN[i] : rho_a;
+            int ki = g.ckey[i];
+            cxi = ki - rowbase;
+            cs_a = g.cell_start[ki];
+            ce_a = g.cell_start[ki + 1];
+        }
+        PairSide<T, D> sa;   // GENERIC only
+        PairAccum<T, D> sacc;
+        accum_zero(sacc);
+        if (GENERIC) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                sa.x[k] = xa[k];
+                sa.v[k] = va[k];
+                sa.vn[k] = va[k];
+            }
+            sa.rho = rho_a;
+            sa.P = P_a;
+            sa.rho_n = rhon_a;
+            sa.ml = ml_a;
+            if (use_sps && valid) {
+                T dummy_x[D], rs, Pd;
+                L::unpack(g.An_rw[i], g.Bn_rw[i], dummy_x, sa.vn, rs, Pd);
+            }
+        }
+        T drho = T(0), acc[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) acc[k] = T(0);
+        int cnt = 0;   // entries in this thread's list (COMPACT)
+
+        // pair body for one staged candidate (smem slot sj), shared by both phases
+        auto pair_body = [&](int sj, bool a_is_i) {
+            T xb[D], vb[D], rsb, P_b;
+            L::unpack(sA[sj], sB[sj], xb, vb, rsb, P_b);
+            T rho_b = sph_abs(rsb);
+            T ml_b = rsb > T(0) ? T(1) : T(0);
+            T rhon_b = PASS ? sR[sj] : rho_b;
+            T xab[D], r2 = T(0);
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                xab[k] = xa[k] - xb[k];
+                r2 += xab[k] * xab[k];
+            }
+            if (!GENERIC) {
+                pair_fast<T, D>(ph, xab, r2, va, vb, rho_a, rho_b, P_a, P_b, rhon_a, rhon_b, ml_a * ml_b, a_is_i,
+                                drho, acc);
+            } else {
+                PairSide<T, D> sb;
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    sb.x[k] = xb[k];
+                    sb.v[k] = vb[k];
+                    sb.vn[k] = vb[k];
+                }
+                sb.rho = rho_b;
+                sb.P = P_b;
+                sb.rho_n = rhon_b;
+                sb.ml = ml_b;
+                if (use_sps) {
+                    L::vel(sBn[sj], sb.vn);
+                }
+                pair_generic<T, D>(ph, sa, sb, xab, r2, a_is_i, sacc);
+            }
+        };
+        auto flush = [&]() {
+            if (COMPACT) {
+                int m = warp_max(cnt);
+                for (int k = 0; k < m; ++k) {
+                    if (k < cnt) {
+                        unsigned e = slist[k * BT + tid];
+                        pair_body((int)(e & (ROLE_BIT - 1)), (e & ROLE_BIT) != 0);
+                    }
+                }
+                cnt = 0;
+            }
+        };
+
+        // ---- stages: the concatenated candidate sequence in pieces of <= cap -----------------
+        for (int s0 = 0; s0 < total; s0 += cap) {
+            const int s1 = min(s0 + cap, total);
+            if (g.use_tma) {
+                if (tid == 0) {
+                    uint32_t bytes = 0;
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) {
+                        int lo = max(s_off[r], s0), hi = min(s_off[r + 1], s1);
+                        if (lo < hi) bytes += (uint32_t)(hi - lo) * (uint32_t)SS::per_candidate;
+                    }
+                    if (!use_sps) bytes -= (uint32_t)(s1 - s0) * (uint32_t)SS::esBn;
+                    mbar_arrive_expect_tx(&s_bar, bytes);
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) {
+                        int lo = max(s_off[r], s0), hi = min(s_off[r + 1], s1);
+                        if (lo < hi) {
+                            int n = hi - lo;
+                            size_t src = (size_t)s_w0a[r] + (size_t)(lo - s_off[r]);
+                            int dst = lo - s0;
+                            tma_load_1d(sA + dst, g.A + src, (uint32_t)n * SS::esA, &s_bar);
+                            tma_load_1d(sB + dst, g.B + src, (uint32_t)n * SS::esB, &s_bar);
+                            if (PASS) tma_load_1d(sR + dst, g.RN + src, (uint32_t)n * SS::esR, &s_bar);
+                            if (use_sps) tma_load_1d(sBn + dst, g.Bn + src, (uint32_t)n * SS::esBn, &s_bar);
+                        }
+                    }
+                }
+                mbar_wait(&s_bar, phase);
+                phase ^= 1u;
+            } else {
+                for (int r = 0; r < NR; ++r) {
+                    int lo = max(s_off[r], s0), hi = min(s_off[r + 1], s1);
+                    size_t src = (size_t)s_w0a[r] + (size_t)(lo - s_off[r]);
+                    int dst = lo - s0;
+                    for (int k = tid; k < hi - lo; k += BT) {
+                        sA[dst + k] = g.A[src + k];
+                        sB[dst + k] = g.B[src + k];
+                        if (PASS) sR[dst + k] = g.RN[src + k];
+                        if (use_sps) sBn[dst + k] = g.Bn[src + k];
+                    }
+                }
+                __syncthreads();
+            }
+
+            // ---- phase 1 (+ phase 2 when lists fill): walk the rows of this stage ------------
+            for (int r = 0; r < NR; ++r) {
+                const int lo_s = max(s_off[r], s0), hi_s = min(s_off[r + 1], s1);
+                if (lo_s >= hi_s) continue;
+                const int dm = (D == 3) ? (r % 3 - 1) : 0;
+                const int ds = (D == 3) ? (r / 3 - 1) : (r - 1);
+                const int rk = rowbase + (ds * nm + dm) * nx;
+                // this lane's window in row r: cells cx-1 .. cx+1 (stale cells, exact pair set)
+                int lo = 0, hi = 0;
+                if (valid) {
+                    lo = g.cell_start[rk + cxi - 1];
+                    hi = g.cell_start[rk + cxi + 2];
+                }
+                // role of the row: +1 b's row is lower in the reference's cell order
+                // (a is "i"), -1 higher (a is "j"), 0 same row (decided per candidate)
+                int major = g.ref_major_is_s ? ds : dm;
+                int minor = g.ref_major_is_s ? dm : ds;
+                int rowrole = major != 0 ? -major : -minor;
+                // staged global index range of this row in this stage
+                const int jbase = s_w0a[r] - s_off[r];   // global j = staged position + jbase
+                int jb = lo_s + jbase, je = hi_s + jbase;
+                // clip to the union of the warp's lane windows (windows are monotone in i)
+                int ulo = warp_min(valid ? lo : INT_MAX);
+                int uhi = warp_max(valid ? hi : INT_MIN);
+                jb = max(jb, ulo);
+                je = min(je, uhi);
+                const int sbase = -jbase - s0;          // smem slot = j + sbase
+                for (int j4 = jb; j4 < je; j4 += 4) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = j4 + u;
+                        if (j < je) {
+                            const int sj = j + sbase;
+                            T xb[D];
+                            L::pos(sA[sj], xb);
+                            T r2 = T(0);
+#pragma unroll
+                            for (int k = 0; k < D; ++k) {
+                                T dlt = xa[k] - xb[k];
+                                r2 += dlt * dlt;
+                            }
+                            bool ok = (j >= lo) & (j < hi) & (r2 <= ph.H2) & (j != i);
+                            if (ok) {
+                                bool a_is_i = rowrole > 0 || (rowrole == 0 && ((j < cs_a) || (j > i && j < ce_a)));
+                                if (COMPACT) {
+                                    slist[cnt * BT + tid] = (unsigned short)(sj | (a_is_i ? ROLE_BIT : 0));
+                                    ++cnt;
+                                } else {
+                                    pair_body(sj, a_is_i);
+                                }
+                            }
+                        }
+                    }
+                    if (COMPACT) {
+                        if (__any_sync(0xffffffffu, cnt > LIST_CAP - 4)) flush();
+                    }
+                }
+            }
+            flush();
+            __syncthreads();   // everyone is done with this stage's shared memory
+        }
+
+        // ---- epilogue ---------------------------------------------------------------------
+        if (valid) {
+            if (GENERIC) {
+                drho = sacc.drho;
+#pragma unroll
+                for (int k = 0; k < D; ++k) acc[k] = sacc.acc[k];
+                if (ph.shifting) {
+                    g.gradC[i] = L::mkv(sacc.gradC);
+                    g.divr[i] = sacc.divr;
+                }
+                if (ph.kernel_output) {
+                    g.ksum[i] = sacc.ksum;
+                    g.kgrad[i] = L::mkv(sacc.kgrad);
+                }
+            }
+            if (g.epilogue == EPI_STORE) {
+                g.drhodt[i] = drho;
+                g.acc[i] = L::mkv(acc);
+            } else {
+                const uint8_t ty = g.type[i];
+                const T gf = (T)type_gf(ty), ml = (T)type_ml(ty);
+                if (PASS == 0) {
+                    // HalfTimeStep + LimitDensityAtBoundary!(ρₙ⁺) + Pressure!(ρₙ⁺)  (S9, S10, S13)
+                    const T dt2 = (T)g.ctl->dt2;
+                    T xh[D], vh[D], rhoh;
+                    half_step<T, D>(ph, xa, va, acc, rho_a, drho, gf, ml, dt2, xh, vh, rhoh);
+                    TA oa;
+                    TB ob;
+                    L::pack(oa, ob, xh, vh, ml > T(0) ? rhoh : -rhoh, eos_gamma7(ph, rhoh));
+                    g.Ah_out[i] = oa;
+                    g.Bh_out[i] = ob;
+                } else {
+                    // LimitDensityAtBoundary!(ρ) + DensityEpsi! + FullTimeStep + Pressure!  (S16-S18, S5)
+                    const T dt = (T)g.ctl->dt;
+                    T xn[D], vn[D], rs, Pn;
+                    L::unpack(g.An_rw[i], g.Bn_rw[i], xn, vn, rs, Pn);
+                    T rho = sph_abs(rs);
+                    T gc[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) gc[k] = GENERIC ? sacc.gradC[k] : T(0);
+                    full_step<T, D>(ph, xn, vn, acc, rho, drho, rho_a, gf, ml, dt, gc, GENERIC ? sacc.divr : T(0));
+                    TA oa;
+                    TB ob;
+                    L::pack(oa, ob, xn, vn, ml > T(0) ? rho : -rho, eos_gamma7(ph, rho));
+                    g.An_rw[i] = oa;
+                    g.Bn_rw[i] = ob;
+                    g.acc[i] = L::mkv(acc);
+                }
+            }
+        }
+        __syncthreads();   // s_brick / s_off reuse
+    }
+}
+
+}  // namespace sph

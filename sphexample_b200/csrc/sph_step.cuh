@@ -1,0 +1,368 @@
+// sph_step.cuh — the streaming kernels of one SimulationLoop iteration
+// (src/SPHCellList.jl:742-802): Δt / Δx reductions and the step control block, ProgressMotion,
+// Pressure!, the stand-alone half/full updates (the fused versions live in the interaction
+// kernel's epilogue) and the mDBC ghost-node correction.
+#pragma once
+
+#include "sph_device.cuh"
+
+namespace sph {
+
+// ---------------------------------------------------------------------------------------------
+// S0 + S1: device-wide reductions for update_delta_x! (src/SPHCellList.jl:706-724) and Δt
+// (src/TimeStepping.jl:24-46, Q3: absolute positions, every particle type).
+//   red_disp2 = max ‖xₙ⁺ - x‖²      red_visc = max |h v·x / (x·x + η²)|      red_acc2 = max ‖a‖²
+// min over i of sqrt(h/‖aᵢ‖) == sqrt(h / max ‖aᵢ‖) (monotone), so one max serves.
+// warp shuffle -> one atomicMax per warp on the bit pattern (all three are non-negative).
+// ---------------------------------------------------------------------------------------------
+template <class T, int D>
+__global__ void k_reduce_dt_dx(const typename Lay<T, D>::TA *__restrict__ A, const typename Lay<T, D>::TB *__restrict__ B,
+                               const typename Lay<T, D>::TA *__restrict__ Ah,
+                               const typename Lay<T, D>::TV *__restrict__ acc, int p0, int p1, T h, T eta2,
+                               int have_half, Ctl *ctl) {
+    using L = Lay<T, D>;
+    if (ctl->error || ctl->done) return;
+    T mdisp = T(0), mvisc = T(0), macc = T(0);
+    bool nan = false;
+    for (int i = p0 + blockIdx.x * blockDim.x + threadIdx.x; i < p1; i += gridDim.x * blockDim.x) {
+        T x[D], v[D], rs, P, a[D];
+        L::unpack(A[i], B[i], x, v, rs, P);
+        L::getv(acc[i], a);
+        T vx = T(0), xx = T(0), aa = T(0), dd = T(0);
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            vx += v[k] * x[k];
+            xx += x[k] * x[k];
+            aa += a[k] * a[k];
+        }
+        if (have_half) {
+            T xh[D];
+            L::pos(Ah[i], xh);
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                T d = xh[k] - x[k];
+                dd += d * d;
+            }
+        }
+        T visc = sph_abs(h * vx / (xx + eta2));
+        nan |= !(visc == visc) || !(aa == aa) || !(dd == dd);
+        mdisp = sph_max(mdisp, dd);
+        mvisc = sph_max(mvisc, visc);
+        macc = sph_max(macc, aa);
+    }
+    mdisp = warp_max(mdisp);
+    mvisc = warp_max(mvisc);
+    macc = warp_max(macc);
+    nan = __any_sync(0xffffffffu, nan);
+    if ((threadIdx.x & 31) == 0) {
+        if (nan) {
+            atomicCAS(&ctl->error, 0, SPH_ERR_ENUMERIC);
+        } else {
+            if (mdisp > T(0)) atomic_max_nonneg(&ctl->red_disp2, (double)mdisp);
+            if (mvisc > T(0)) atomic_max_nonneg(&ctl->red_visc, (double)mvisc);
+            if (macc > T(0)) atomic_max_nonneg(&ctl->red_acc2, (double)macc);
+        }
+    }
+}
+
+// One thread.  Finishes S0/S1, decides S2 (src/SPHCellList.jl:744-762) and the while-condition
+// (:742).  Arithmetic is carried out in T like the reference's (its scalars are ::T).
+template <class T>
+__global__ void k_step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl) {
+    if (ctl->error) return;
+    // consume the reductions unconditionally so that nothing stale survives a skipped step
+    T disp = sph_sqrt((T)bits_to_double(ctl->red_disp2));
+    T visc = (T)bits_to_double(ctl->red_visc);
+    T acc2 = (T)bits_to_double(ctl->red_acc2);
+    ctl->red_disp2 = 0ull;
+    ctl->red_visc = 0ull;
+    ctl->red_acc2 = 0ull;
+    if (ctl->use_target && !(ctl->total_time <= ctl->target_time)) {
+        ctl->done = 1;
+        return;
+    }
+    if (ctl->done) return;
+    ctl->delta_x = (double)((T)ctl->delta_x + T(4) * disp);
+    T dt1 = sph_sqrt(h / sph_sqrt(acc2));   // +inf when every acceleration is zero (first step)
+    T dt2 = h / (c0 + visc);
+    T dt = cfl * sph_min(dt1, dt2);
+    if (!(dt > T(0)) || !(dt < T(1e30))) {
+        ctl->error = SPH_ERR_ENUMERIC;
+        return;
+    }
+    ctl->dt = (double)dt;
+    ctl->dt2 = (double)(dt * T(0.5));
+    if ((T)ctl->delta_x >= h) {
+        ctl->do_rebuild = 1;
+        ctl->delta_x = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            grid->bb_min[k] = INT_MAX;
+            grid->bb_max[k] = INT_MIN;
+        }
+    }
+    ctl->red_disp2 = 0ull;
+    ctl->red_visc = 0ull;
+    ctl->red_acc2 = 0ull;
+    ctl->work_counter[0] = 0;
+    ctl->work_counter[1] = 0;
+    ctl->step_open = 1;
+}
+
+// UpdateMetaData!, src/SPHCellList.jl:679-685 (S19)
+__global__ void k_step_end(Ctl *ctl) {
+    if (ctl->error || ctl->done || !ctl->step_open) return;
+    ctl->iteration += 1;
+    ctl->current_dt = ctl->dt;
+    ctl->total_time += ctl->dt;
+    ctl->step_open = 0;
+}
+
+__global__ void k_reset_counters(Ctl *ctl) {
+    ctl->work_counter[0] = 0;
+    ctl->work_counter[1] = 0;
+}
+
+// snapshot of ρₙ for the pass-2 diffusion / viscosity terms (Q2)
+template <class T, int D>
+__global__ void k_snapshot_rho(const typename Lay<T, D>::TA *__restrict__ A, T *__restrict__ RN, int n, const Ctl *ctl) {
+    if (ctl->error || ctl->done) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        RN[i] = sph_abs(Lay<T, D>::rhos(A[i]));
+}
+
+// Pressure!(P, ρ), src/SimulationEquations.jl:18-24
+template <class T, int D>
+__global__ void k_pressure(typename Lay<T, D>::TA *A, typename Lay<T, D>::TB *B, int n, Phys<T> ph, const Ctl *ctl) {
+    if (ctl->error || ctl->done) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        typename Lay<T, D>::TA a = A[i];
+        typename Lay<T, D>::TB b = B[i];
+        Lay<T, D>::set_P(a, b, eos_gamma7(ph, sph_abs(Lay<T, D>::rhos(a))));
+        A[i] = a;
+        B[i] = b;
+    }
+}
+
+// ProgressMotion, src/SPHCellList.jl:575-596 (Q8): Moving particles only, uses TotalTime of the
+// step start.  dt2 < 0 means "read ctl->dt2".
+struct MotionTable {
+    int n;
+    unsigned long long group[16];
+    double velocity[16], start[16], duration[16], dir[16][3];
+};
+
+template <class T, int D>
+__global__ void k_progress_motion(typename Lay<T, D>::TA *A, typename Lay<T, D>::TB *B, const uint8_t *__restrict__ type,
+                                  const unsigned long long *__restrict__ group, int n, MotionTable mt, double dt2_arg,
+                                  const Ctl *ctl) {
+    using L = Lay<T, D>;
+    if (ctl->error || ctl->done) return;
+    const T dt2 = (T)(dt2_arg < 0.0 ? ctl->dt2 : dt2_arg);
+    const T tnow = (T)ctl->total_time;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (type[i] != 3) continue;
+        int m = -1;
+        for (int k = 0; k < mt.n; ++k)
+            if (mt.group[k] == group[i]) m = k;
+        if (m < 0) continue;
+        T st = (T)mt.start[m], du = (T)mt.duration[m];
+        T should = (st <= tnow && tnow <= (st + du)) ? T(1) : T(0);
+        T x[D], v[D], rs, P;
+        typename L::TA a = A[i];
+        typename L::TB b = B[i];
+        L::unpack(a, b, x, v, rs, P);
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            v[k] = (T)mt.velocity[m] * (T)mt.dir[m][k] * should;
+            x[k] += v[k] * dt2;
+        }
+        L::pack(a, b, x, v, rs, P);
+        A[i] = a;
+        B[i] = b;
+    }
+}
+
+// stand-alone HalfTimeStep + LimitDensityAtBoundary!(ρₙ⁺) (+ Pressure!(ρₙ⁺)), S9/S10/S13
+template <class T, int D>
+__global__ void k_half_step(const typename Lay<T, D>::TA *__restrict__ A, const typename Lay<T, D>::TB *__restrict__ B,
+                            typename Lay<T, D>::TV *acc, const T *__restrict__ drhodt, const uint8_t *__restrict__ type,
+                            typename Lay<T, D>::TA *Ah, typename Lay<T, D>::TB *Bh, int p0, int p1, Phys<T> ph,
+                            double dt2_arg, const Ctl *ctl) {
+    using L = Lay<T, D>;
+    if (ctl->error || ctl->done) return;
+    const T dt2 = (T)(dt2_arg < 0.0 ? ctl->dt2 : dt2_arg);
+    for (int i = p0 + blockIdx.x * blockDim.x + threadIdx.x; i < p1; i += gridDim.x * blockDim.x) {
+        T x[D], v[D], rs, P, a[D];
+        L::unpack(A[i], B[i], x, v, rs, P);
+        L::getv(acc[i], a);
+        const uint8_t ty = type[i];
+        const T gf = (T)type_gf(ty), ml = (T)type_ml(ty);
+        T xh[D], vh[D], rhoh;
+        half_step<T, D>(ph, x, v, a, sph_abs(rs), drhodt[i], gf, ml, dt2, xh, vh, rhoh);
+        acc[i] = L::mkv(a);
+        typename L::TA oa;
+        typename L::TB ob;
+        L::pack(oa, ob, xh, vh, ml > T(0) ? rhoh : -rhoh, eos_gamma7(ph, rhoh));
+        Ah[i] = oa;
+        Bh[i] = ob;
+    }
+}
+
+// stand-alone LimitDensityAtBoundary!(ρ) + DensityEpsi! + FullTimeStep (+ Pressure!(ρ)), S16-S18
+template <class T, int D>
+__global__ void k_full_step(typename Lay<T, D>::TA *A, typename Lay<T, D>::TB *B, typename Lay<T, D>::TV *acc,
+                            const T *__restrict__ drhodt, const typename Lay<T, D>::TA *__restrict__ Ah,
+                            const uint8_t *__restrict__ type, const typename Lay<T, D>::TV *__restrict__ gradC,
+                            const T *__restrict__ divr, int p0, int p1, Phys<T> ph, double dt_arg, const Ctl *ctl) {
+    using L = Lay<T, D>;
+    if (ctl->error || ctl->done) return;
+    const T dt = (T)(dt_arg < 0.0 ? ctl->dt : dt_arg);
+    for (int i = p0 + blockIdx.x * blockDim.x + threadIdx.x; i < p1; i += gridDim.x * blockDim.x) {
+        T x[D], v[D], rs, P, a[D], gc[D];
+        L::unpack(A[i], B[i], x, v, rs, P);
+        L::getv(acc[i], a);
+        const uint8_t ty = type[i];
+        const T gf = (T)type_gf(ty), ml = (T)type_ml(ty);
+        T rho = sph_abs(rs);
+        T rhoh = sph_abs(L::rhos(Ah[i]));
+        T dv = T(0);
+#pragma unroll
+        for (int k = 0; k < D; ++k) gc[k] = T(0);
+        if (ph.shifting) {
+            L::getv(gradC[i], gc);
+            dv = divr[i];
+        }
+        full_step<T, D>(ph, x, v, a, rho, drhodt[i], rhoh, gf, ml, dt, gc, dv);
+        typename L::TA oa;
+        typename L::TB ob;
+        L::pack(oa, ob, x, v, ml > T(0) ? rho : -rho, eos_gamma7(ph, rho));
+        A[i] = oa;
+        B[i] = ob;
+        acc[i] = L::mkv(a);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ApplyMDBCBeforeHalf!, src/SPHCellList.jl:219-266,319-365,491-505,598-622 (S6).  One thread per
+// boundary particle that has a ghost node: gather fluid neighbours of the ghost node over the
+// full 3^D stencil of the ghost node's cell, build b (D+1) and A (D+1)², solve in registers.
+// Two phases like the reference: new densities go to `rho_new` first (k_mdbc_gather), then are
+// applied (k_mdbc_apply) so that no thread reads a density another thread has just corrected.
+// ---------------------------------------------------------------------------------------------
+template <class T, int D>
+__global__ void k_mdbc_gather(const typename Lay<T, D>::TA *__restrict__ A, const typename Lay<T, D>::TV *__restrict__ ghost,
+                              const uint8_t *__restrict__ type, const int *__restrict__ cell_start, const GridInfo *grid,
+                              AxisMap am, int n, Phys<T> ph, double inv_cutoff, T *__restrict__ rho_new,
+                              uint8_t *__restrict__ has_new, const Ctl *ctl) {
+    using L = Lay<T, D>;
+    constexpr int E = D + 1;
+    if (ctl->error || ctl->done) return;
+    const int nx = grid->nx, nm = grid->nm, ns = grid->ns;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        has_new[i] = 0;
+        T gp[D];
+        L::getv(ghost[i], gp);
+        bool zero = true;
+#pragma unroll
+        for (int k = 0; k < D; ++k) zero &= (gp[k] == T(0));
+        if (zero) continue;   // Q10 sentinel: "no ghost node"
+        int bad = 0;
+        int gc[3] = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < D; ++k) gc[k] = map_floor_dev((double)gp[k], inv_cutoff, bad);
+        int cx = gc[0] - grid->cmin[0];
+        int cm = (D == 3) ? gc[am.ax_m] - grid->cmin[am.ax_m] : 0;
+        int cs = gc[am.ax_s] - grid->cmin[am.ax_s];
+        double bv[E], Am[E][E];
+        for (int r = 0; r < E; ++r) {
+            bv[r] = 0.0;
+            for (int c = 0; c < E; ++c) Am[r][c] = 0.0;
+        }
+        for (int ds = -1; ds <= 1; ++ds)
+            for (int dm = (D == 3 ? -1 : 0); dm <= (D == 3 ? 1 : 0); ++dm) {
+                int rs_ = cs + ds, rm = cm + dm;
+                if (rs_ < 0 || rs_ >= ns || rm < 0 || rm >= nm) continue;
+                int x0 = max(cx - 1, 0), x1 = min(cx + 1, nx - 1);
+                if (x0 > x1) continue;
+                int rk = (rs_ * nm + rm) * nx;
+                int jb = cell_start[rk + x0], je = cell_start[rk + x1 + 1];
+                for (int j = jb; j < je; ++j) {
+                    if (type[j] != 1) continue;
+                    typename L::TA aj = A[j];
+                    T xj[D];
+                    L::pos(aj, xj);
+                    T xij[D], r2 = T(0);
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        xij[k] = gp[k] - xj[k];
+                        r2 += xij[k] * xij[k];
+                    }
+                    if (!(r2 <= ph.H2)) continue;
+                    T d = sph_sqrt(sph_abs(r2));
+                    T q = sph_min(sph_max(d * ph.h_inv, T(0)), T(2));
+                    T W = kernel_w(ph, q);
+                    T gW[D];
+                    if (ph.kernel == K_WENDLAND) {
+                        T qm2 = q - T(2);
+                        T fac = ph.gradw_c * (qm2 * qm2 * qm2);
+#pragma unroll
+                        for (int k = 0; k < D; ++k) gW[k] = fac * xij[k];
+                    } else {
+                        T dwdq = (q <= T(1)) ? ph.alphaD * (T(-3) * q + T(2.25) * (q * q))
+                                             : ph.alphaD * T(-0.75) * ((T(2) - q) * (T(2) - q));
+                        T sc = dwdq * ph.h_inv;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) gW[k] = sc * xij[k] / (d + ph.eta2);
+                    }
+                    T Vj = ph.m0 / sph_abs(L::rhos(aj));
+                    double col[E];
+                    col[0] = (double)(Vj * W);
+                    bv[0] += (double)(ph.m0 * W);
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        col[k + 1] = (double)(Vj * gW[k]);
+                        bv[k + 1] += (double)(ph.m0 * gW[k]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < E; ++r) {
+                        Am[r][0] += col[r];
+#pragma unroll
+                        for (int c = 1; c < E; ++c) Am[r][c] += (double)(-xij[c - 1]) * col[r];
+                    }
+                }
+            }
+        double detA = det_lu<E>(Am);
+        T xi[D];
+        L::pos(A[i], xi);
+        if (fabs(detA) >= 1e-3) {
+            double sol[E];
+            solve_lu<E>(Am, bv, sol);
+            double v1 = sol[0];
+#pragma unroll
+            for (int k = 0; k < D; ++k) v1 += sol[k + 1] * ((double)xi[k] - (double)gp[k]);
+            rho_new[i] = (v1 == v1) ? (T)v1 : ph.rho0;
+            has_new[i] = 1;
+        } else if (Am[0][0] > 0.0) {
+            double v = bv[0] / Am[0][0];
+            rho_new[i] = (v == v) ? (T)v : ph.rho0;
+            has_new[i] = 1;
+        }
+    }
+}
+
+template <class T, int D>
+__global__ void k_mdbc_apply(typename Lay<T, D>::TA *A, T *RN, const uint8_t *__restrict__ type,
+                             const T *__restrict__ rho_new, const uint8_t *__restrict__ has_new, int n, const Ctl *ctl) {
+    using L = Lay<T, D>;
+    if (ctl->error || ctl->done) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (!has_new[i]) continue;
+        typename L::TA a = A[i];
+        T r = rho_new[i];
+        L::set_rhos(a, type[i] == 1 ? r : -r);
+        A[i] = a;
+        RN[i] = r;
+    }
+}
+
+}  // namespace sph

@@ -1,0 +1,1136 @@
+// sphb200.cu — host side of libsphb200.so: the C-ABI of include/sphb200.h on top of the sm_100a
+// kernels in sph_cells.cuh / sph_interact.cuh / sph_step.cuh.
+//
+// One handle = one CUDA device + one stream.  The step sequence of SimulationLoop
+// (src/SPHCellList.jl:742-802) is enqueued without host round trips: Δt, Δx, the rebuild
+// decision and the loop condition live in a device-resident control block (sph::Ctl), rebuild
+// kernels are predicated on it, and the host only synchronises once per batch of steps.
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/sphb200.h"
+#include "sph_cells.cuh"
+#include "sph_interact.cuh"
+#include "sph_slab.cuh"
+#include "sph_step.cuh"
+
+using namespace sph;
+
+static thread_local std::string g_create_error;
+
+struct sphb200_sim {
+    std::string err;
+    virtual ~sphb200_sim() {}
+    virtual int upload(int64_t n, const void *pos, const void *vel, const void *acc, const void *rho, const uint8_t *type,
+                       const uint64_t *group, const int64_t *id, const void *ghost, const void *gnorm) = 0;
+    virtual int download(int order, void *pos, void *vel, void *acc, void *rho, void *press, int64_t *id, uint8_t *type,
+                         uint64_t *group, int64_t *cells) = 0;
+    virtual int64_t num_particles() const = 0;
+    virtual int set_time(double t, int64_t it) = 0;
+    virtual int simulation_loop(double t_next, sphb200_report *rep) = 0;
+    virtual int step(int64_t n, int reset_dx, sphb200_report *rep) = 0;
+    virtual int get_report(sphb200_report *rep) = 0;
+    virtual int64_t launch_count() const = 0;
+    virtual int update_neighbors(int64_t *index_counter) = 0;
+    virtual int get_cell_list(int64_t *n_cells, int64_t *cells, int64_t *start) = 0;
+    virtual int pressure(int half) = 0;
+    virtual int neighbor_loop(int pass, void *drhodt_out, void *acc_out) = 0;
+    virtual int delta_t(double *dt) = 0;
+    virtual int progress_motion(double dt2) = 0;
+    virtual int apply_mdbc() = 0;
+    virtual int half_time_step(double dt2) = 0;
+    virtual int full_time_step(double dt) = 0;
+    virtual int download_half(void *ph, void *vh, void *rh, void *prh) = 0;
+    virtual int download_aux(void *gradc, void *divr, void *ksum, void *kgrad) = 0;
+    virtual int set_stream(void *stream) = 0;
+    virtual int set_option(const char *name, double value) = 0;
+    virtual int comm_init(const uint8_t *id, int rank, int world, int axis) = 0;
+    virtual int set_slab(int64_t lo, int64_t hi) = 0;
+    virtual int column_histogram(int axis, int64_t *cell_min, int64_t *n_columns, int64_t *counts, int64_t cap) = 0;
+    virtual int stage_times(double *ms_out, int n) = 0;
+};
+
+namespace {
+
+static int env_int(const char *name, int dflt) {
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+template <class T, int D>
+__global__ void k_pack_upload(int n, const T *__restrict__ pos, const T *__restrict__ vel, const T *__restrict__ acc,
+                              const T *__restrict__ rho, const T *__restrict__ ghost, const uint8_t *__restrict__ type,
+                              Phys<T> ph, typename Lay<T, D>::TA *A, typename Lay<T, D>::TB *B,
+                              typename Lay<T, D>::TV *accv, typename Lay<T, D>::TV *ghostv) {
+    using L = Lay<T, D>;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        T x[D], v[D], a[D], gp[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            x[k] = pos[(size_t)i * D + k];
+            v[k] = vel ? vel[(size_t)i * D + k] : T(0);
+            a[k] = acc ? acc[(size_t)i * D + k] : T(0);
+            gp[k] = ghost ? ghost[(size_t)i * D + k] : T(0);
+        }
+        T r = rho[i];
+        typename L::TA oa;
+        typename L::TB ob;
+        L::pack(oa, ob, x, v, type[i] == 1 ? r : -r, eos_gamma7(ph, r));   // Pressure! of RunSimulation, :835
+        A[i] = oa;
+        B[i] = ob;
+        accv[i] = L::mkv(a);
+        if (ghostv) ghostv[i] = L::mkv(gp);
+    }
+}
+
+template <class T, int D>
+__global__ void k_unpack_download(int n, const typename Lay<T, D>::TA *__restrict__ A, const typename Lay<T, D>::TB *__restrict__ B,
+                                  const typename Lay<T, D>::TV *__restrict__ accv, T *pos, T *vel, T *acc, T *rho, T *press) {
+    using L = Lay<T, D>;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        T x[D], v[D], a[D], rs, P;
+        L::unpack(A[i], B[i], x, v, rs, P);
+#pragma unroll
+        for (int k = 0; k < D; ++k) a[k] = T(0);
+        if (accv) L::getv(accv[i], a);
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            if (pos) pos[(size_t)i * D + k] = x[k];
+            if (vel) vel[(size_t)i * D + k] = v[k];
+            if (acc) acc[(size_t)i * D + k] = a[k];
+        }
+        if (rho) rho[i] = sph_abs(rs);
+        if (press) press[i] = P;
+    }
+}
+
+template <class T, int D>
+__global__ void k_unpack_vec(int n, const typename Lay<T, D>::TV *__restrict__ src, T *dst) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        T a[D];
+        Lay<T, D>::getv(src[i], a);
+#pragma unroll
+        for (int k = 0; k < D; ++k) dst[(size_t)i * D + k] = a[k];
+    }
+}
+
+template <class T, int D>
+class Sim final : public sphb200_sim {
+    using L = Lay<T, D>;
+    using TA = typename L::TA;
+    using TB = typename L::TB;
+    using TV = typename L::TV;
+    static constexpr int BT = 128;
+
+  public:
+    sphb200_params prm;
+    Phys<T> ph;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+    int64_t n = 0;        // particles held (owned + halo)
+    size_t n_alloc = 0;
+    bool have_cells = false, have_half = false, uploaded = false;
+    int64_t launches = 0;
+    // options
+    int opt_compact, opt_tma, opt_smem_kb, opt_batch;
+    bool generic = false;
+    AxisMap am;
+    int ref_major_is_s = 1;
+    int own_lo = INT_MIN, own_hi = INT_MAX;
+    // particle table (cell-sorted) and scratch copy for the reorder
+    DevBuf<TA> A, A2, Ah;
+    DevBuf<TB> B, B2, Bh;
+    DevBuf<TV> acc, acc2, ghost, ghost2, gradC, kgrad;
+    DevBuf<T> RN, drhodt, divr, ksum, rho_new;
+    DevBuf<long long> id, id2;
+    DevBuf<unsigned long long> group, group2;
+    DevBuf<uint8_t> type, type2, has_new;
+    DevBuf<int> ckey, ckey2, ccoord, key_tmp, slot_tmp, tmp_idx, perm;
+    // cell structure
+    DevBuf<int> cell_count, cell_start, scan_partial;
+    DevBuf<Brick> bricks;
+    long long cell_cap = 0, row_cap = 0;
+    int brick_cap = 0;
+    DevBuf<Ctl> d_ctl;
+    DevBuf<GridInfo> d_grid;
+    Ctl *h_ctl = nullptr;        // pinned mirrors
+    GridInfo *h_grid = nullptr;
+    DevBuf<unsigned char> stage;   // raw staging for upload / download
+    MotionTable motions;
+    SlabComm slab;
+
+    Sim(const sphb200_params &p, int dev) : prm(p), device(dev) {
+        opt_compact = env_int("SPHB200_COMPACT", 1);
+        opt_tma = env_int("SPHB200_TMA", 1);
+        opt_smem_kb = env_int("SPHB200_SMEM_KB", 96);
+        opt_batch = env_int("SPHB200_BATCH", 64);
+        am.ax_s = D - 1;   // default: the reference's most significant axis
+        am.ax_m = (D == 3) ? 1 : 0;
+        build_phys();
+    }
+    ~Sim() override {
+        if (h_ctl) cudaFreeHost(h_ctl);
+        if (h_grid) cudaFreeHost(h_grid);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+
+    int fail(int code, const char *fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(SPHB200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+    void build_phys() {
+        const sphb200_params &p = prm;
+        ph = phys_from_params<T>(p);
+        generic = !(p.kernel == SPHB200_KERNEL_WENDLANDC2 && p.viscosity == SPHB200_VISC_ARTIFICIAL &&
+                    p.diffusion == SPHB200_DDT_LINEAR && !p.shifting && !p.kernel_output);
+        memset(&motions, 0, sizeof motions);
+        motions.n = p.n_motions;
+        for (int k = 0; k < p.n_motions && k < SPHB200_MAX_MOTIONS; ++k) {
+            motions.group[k] = (unsigned long long)p.motions[k].group_marker;
+            motions.velocity[k] = p.motions[k].velocity;
+            motions.start[k] = p.motions[k].start_time;
+            motions.duration[k] = p.motions[k].duration;
+            for (int d = 0; d < 3; ++d) motions.dir[k][d] = p.motions[k].direction[d];
+        }
+    }
+
+    int init() {
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10)
+            return fail(SPHB200_ECUDA, "device %d is sm_%d%d; libsphb200 is built for sm_100a only", device, prop.major, prop.minor);
+        num_sms = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        own_stream = true;
+        CK(d_ctl.alloc(1));
+        CK(d_grid.alloc(1));
+        CK(cudaMallocHost((void **)&h_ctl, sizeof(Ctl)));
+        CK(cudaMallocHost((void **)&h_grid, sizeof(GridInfo)));
+        memset(h_ctl, 0, sizeof(Ctl));
+        memset(h_grid, 0, sizeof(GridInfo));
+        CK(cudaMemcpyAsync(d_ctl.p, h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_grid.p, h_grid, sizeof(GridInfo), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        return SPHB200_OK;
+    }
+
+    int set_stream(void *s) override {
+        CK(cudaSetDevice(device));
+        CK(cudaStreamSynchronize(stream));
+        if (own_stream && stream) cudaStreamDestroy(stream);
+        stream = (cudaStream_t)s;
+        own_stream = false;
+        return SPHB200_OK;
+    }
+    int set_option(const char *name, double value) override {
+        std::string k(name ? name : "");
+        if (k == "compact") opt_compact = (int)value;
+        else if (k == "tma") opt_tma = (int)value;
+        else if (k == "smem_kb") opt_smem_kb = (int)value;
+        else if (k == "batch") opt_batch = std::max(1, (int)value);
+        else if (k == "generic") generic = generic || value != 0.0;
+        else return fail(SPHB200_EINVAL, "unknown option '%s'", k.c_str());
+        return SPHB200_OK;
+    }
+
+    int grid_for(int64_t count, int threads = 256) const {
+        int64_t b = (count + threads - 1) / threads;
+        return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)num_sms * 16));
+    }
+
+    // ------------------------------------------------------------------ allocation
+    int alloc_particles(int64_t count) {
+        size_t na = (size_t)((count + 3) & ~3ll) + 8;
+        if (na <= n_alloc) return SPHB200_OK;
+        na = na + na / 8;   // headroom for slab migration
+        CK(A.alloc(na)); CK(A2.alloc(na)); CK(Ah.alloc(na));
+        CK(B.alloc(na)); CK(B2.alloc(na)); CK(Bh.alloc(na));
+        CK(acc.alloc(na)); CK(acc2.alloc(na));
+        CK(RN.alloc(na)); CK(drhodt.alloc(na));
+        CK(id.alloc(na)); CK(id2.alloc(na)); CK(group.alloc(na)); CK(group2.alloc(na));
+        CK(type.alloc(na)); CK(type2.alloc(na));
+        CK(ckey.alloc(na)); CK(ckey2.alloc(na)); CK(ccoord.alloc(na * D));
+        CK(key_tmp.alloc(na)); CK(slot_tmp.alloc(na)); CK(tmp_idx.alloc(na)); CK(perm.alloc(na));
+        if (prm.mdbc) { CK(ghost.alloc(na)); CK(ghost2.alloc(na)); CK(rho_new.alloc(na)); CK(has_new.alloc(na)); }
+        if (prm.shifting) { CK(gradC.alloc(na)); CK(divr.alloc(na)); }
+        if (prm.kernel_output) { CK(ksum.alloc(na)); CK(kgrad.alloc(na)); }
+        CK(stage.alloc(na * (size_t)(sizeof(T) * (4 * D + 2) + 8)));
+        // zero everything the TMA staging may touch beyond n (finite padding)
+        CK(cudaMemsetAsync(A.p, 0, na * sizeof(TA), stream)); CK(cudaMemsetAsync(Ah.p, 0, na * sizeof(TA), stream));
+        CK(cudaMemsetAsync(B.p, 0, na * sizeof(TB), stream)); CK(cudaMemsetAsync(Bh.p, 0, na * sizeof(TB), stream));
+        CK(cudaMemsetAsync(RN.p, 0, na * sizeof(T), stream));
+        CK(cudaMemsetAsync(acc.p, 0, na * sizeof(TV), stream));
+        n_alloc = na;
+        return SPHB200_OK;
+    }
+    int alloc_cells(long long cells_needed) {
+        long long cap = std::max<long long>(cells_needed, 4096);
+        if (cap > (1ll << 28)) return fail(SPHB200_ECAPACITY, "cell grid of %lld cells exceeds the dense-grid limit", cap);
+        if (cap <= cell_cap) return SPHB200_OK;
+        CK(cell_count.alloc((size_t)cap + 8));
+        CK(cell_start.alloc((size_t)cap + 8));
+        CK(scan_partial.alloc((size_t)(cap / SCAN_CHUNK + 2)));
+        cell_cap = cap;
+        row_cap = cap / 3 + 1;
+        brick_cap = (int)std::min<long long>((long long)(n_alloc / BT) + row_cap + 16, INT_MAX);
+        CK(bricks.alloc((size_t)brick_cap));
+        return SPHB200_OK;
+    }
+
+    // ------------------------------------------------------------------ state transfer
+    int upload(int64_t count, const void *pos, const void *vel, const void *accel, const void *rho, const uint8_t *ty,
+               const uint64_t *grp, const int64_t *ids, const void *gp, const void *gn) override {
+        (void)gn;
+        if (count < 1 || count > (int64_t)INT_MAX / 8 || !pos || !rho || !ty)
+            return fail(SPHB200_EINVAL, "upload: need n >= 1, position, density and type");
+        CK(cudaSetDevice(device));
+        int rc = alloc_particles(count);
+        if (rc) return rc;
+        n = count;
+        // raw arrays -> staging -> packed layout on the device
+        unsigned char *sp = stage.p;
+        size_t vb = (size_t)count * D * sizeof(T), sb = (size_t)count * sizeof(T);
+        T *d_pos = (T *)sp; sp += vb;
+        T *d_vel = (T *)sp; sp += vb;
+        T *d_acc = (T *)sp; sp += vb;
+        T *d_gp = (T *)sp; sp += vb;
+        T *d_rho = (T *)sp; sp += sb;
+        CK(cudaMemcpyAsync(d_pos, pos, vb, cudaMemcpyHostToDevice, stream));
+        if (vel) CK(cudaMemcpyAsync(d_vel, vel, vb, cudaMemcpyHostToDevice, stream));
+        if (accel) CK(cudaMemcpyAsync(d_acc, accel, vb, cudaMemcpyHostToDevice, stream));
+        if (gp && prm.mdbc) CK(cudaMemcpyAsync(d_gp, gp, vb, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_rho, rho, sb, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(type.p, ty, (size_t)count, cudaMemcpyHostToDevice, stream));
+        if (grp) {
+            CK(cudaMemcpyAsync(group.p, grp, (size_t)count * 8, cudaMemcpyHostToDevice, stream));
+        } else {
+            std::vector<unsigned long long> ones((size_t)count, 1ull);
+            CK(cudaMemcpyAsync(group.p, ones.data(), (size_t)count * 8, cudaMemcpyHostToDevice, stream));
+            CK(cudaStreamSynchronize(stream));
+        }
+        if (ids) {
+            CK(cudaMemcpyAsync(id.p, ids, (size_t)count * 8, cudaMemcpyHostToDevice, stream));
+        } else {
+            std::vector<long long> seq((size_t)count);
+            std::iota(seq.begin(), seq.end(), 1ll);
+            CK(cudaMemcpyAsync(id.p, seq.data(), (size_t)count * 8, cudaMemcpyHostToDevice, stream));
+            CK(cudaStreamSynchronize(stream));
+        }
+        k_pack_upload<T, D><<<grid_for(count), 256, 0, stream>>>((int)count, d_pos, vel ? d_vel : nullptr,
+                                                                accel ? d_acc : nullptr, d_rho,
+                                                                (gp && prm.mdbc) ? d_gp : nullptr, type.p, ph, A.p, B.p,
+                                                                acc.p, prm.mdbc ? ghost.p : nullptr);
+        ++launches;
+        CK(cudaGetLastError());
+        // size the dense cell grid from the host-side bounding box (grown on demand later)
+        {
+            const T *hp = (const T *)pos;
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            for (int64_t i = 0; i < count; ++i)
+                for (int k = 0; k < D; ++k) {
+                    double x = (double)hp[i * D + k];
+                    lo[k] = std::min(lo[k], x);
+                    hi[k] = std::max(hi[k], x);
+                }
+            long long cells = 1;
+            for (int k = 0; k < D; ++k) {
+                double e = (hi[k] - lo[k]) * prm.H_inv + 12.0;
+                if (!(e < 1e9)) return fail(SPHB200_EINVAL, "upload: non-finite or absurd position range");
+                cells *= (long long)e;
+                if (cells > (1ll << 40)) break;
+            }
+            rc = alloc_cells(2 * cells + 1024);
+            if (rc) return rc;
+        }
+        // reset the loop state (a fresh SimParticles table)
+        memset(h_ctl, 0, sizeof(Ctl));
+        CK(cudaMemcpyAsync(d_ctl.p, h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        have_cells = false;
+        have_half = false;
+        uploaded = true;
+        return SPHB200_OK;
+    }
+
+    int download(int order, void *pos, void *vel, void *accel, void *rho, void *press, int64_t *ids, uint8_t *ty,
+                 uint64_t *grp, int64_t *cells) override {
+        if (!uploaded) return fail(SPHB200_ESTATE, "download before upload");
+        CK(cudaSetDevice(device));
+        const int64_t cnt = n;
+        unsigned char *sp = stage.p;
+        size_t vb = (size_t)cnt * D * sizeof(T), sb = (size_t)cnt * sizeof(T);
+        T *d_pos = (T *)sp; sp += vb;
+        T *d_vel = (T *)sp; sp += vb;
+        T *d_acc = (T *)sp; sp += vb;
+        sp += vb;
+        T *d_rho = (T *)sp; sp += sb;
+        T *d_pr = (T *)sp; sp += sb;
+        k_unpack_download<T, D><<<grid_for(cnt), 256, 0, stream>>>((int)cnt, A.p, B.p, acc.p, d_pos, d_vel, d_acc, d_rho, d_pr);
+        ++launches;
+        CK(cudaGetLastError());
+        std::vector<long long> hid((size_t)cnt);
+        CK(cudaMemcpyAsync(hid.data(), id.p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, stream));
+        std::vector<T> hv;
+        std::vector<int64_t> order_idx;
+        CK(cudaStreamSynchronize(stream));
+        if (order == 1) {
+            order_idx.resize((size_t)cnt);
+            std::iota(order_idx.begin(), order_idx.end(), 0);
+            std::stable_sort(order_idx.begin(), order_idx.end(), [&](int64_t a, int64_t b) { return hid[a] < hid[b]; });
+        }
+        auto fetch = [&](void *dst, const void *dsrc, size_t elem, int comps) -> int {
+            if (!dst) return 0;
+            size_t bytes = (size_t)cnt * elem * comps;
+            if (order != 1) {
+                CK(cudaMemcpyAsync(dst, dsrc, bytes, cudaMemcpyDeviceToHost, stream));
+                CK(cudaStreamSynchronize(stream));
+                return 0;
+            }
+            std::vector<unsigned char> tmp(bytes);
+            CK(cudaMemcpyAsync(tmp.data(), dsrc, bytes, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            size_t rb = elem * comps;
+            for (int64_t k = 0; k < cnt; ++k) memcpy((unsigned char *)dst + k * rb, tmp.data() + order_idx[k] * rb, rb);
+            return 0;
+        };
+        int rc;
+        if ((rc = fetch(pos, d_pos, sizeof(T), D))) return rc;
+        if ((rc = fetch(vel, d_vel, sizeof(T), D))) return rc;
+        if ((rc = fetch(accel, d_acc, sizeof(T), D))) return rc;
+        if ((rc = fetch(rho, d_rho, sizeof(T), 1))) return rc;
+        if ((rc = fetch(press, d_pr, sizeof(T), 1))) return rc;
+        if ((rc = fetch(ids, id.p, 8, 1))) return rc;
+        if ((rc = fetch(ty, type.p, 1, 1))) return rc;
+        if ((rc = fetch(grp, group.p, 8, 1))) return rc;
+        if (cells) {
+            // Cells field = CartesianIndex assigned at the last UpdateNeighbors! (stale in between)
+            std::vector<int> hk((size_t)cnt);
+            if (!have_cells) {
+                memset(cells, 0, (size_t)cnt * D * 8);
+            } else {
+                CK(cudaMemcpyAsync(hk.data(), ckey.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, stream));
+                CK(cudaMemcpyAsync(h_grid, d_grid.p, sizeof(GridInfo), cudaMemcpyDeviceToHost, stream));
+                CK(cudaStreamSynchronize(stream));
+                for (int64_t k = 0; k < cnt; ++k) {
+                    int64_t src = order == 1 ? order_idx[k] : k;
+                    int c[3];
+                    key_to_cell(hk[src], c);
+                    for (int d = 0; d < D; ++d) cells[k * D + d] = c[d];
+                }
+            }
+        }
+        return SPHB200_OK;
+    }
+    void key_to_cell(int key, int *c) const {
+        int cx = key % h_grid->nx;
+        int r = key / h_grid->nx;
+        int cm = r % h_grid->nm, cs = r / h_grid->nm;
+        c[0] = cx + h_grid->cmin[0];
+        if (D == 3) c[am.ax_m] = cm + h_grid->cmin[am.ax_m];
+        c[am.ax_s] = cs + h_grid->cmin[am.ax_s];
+    }
+    int64_t num_particles() const override { return n; }
+    int64_t launch_count() const override { return launches; }
+
+    int sync_ctl() {
+        CK(cudaMemcpyAsync(h_ctl, d_ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(h_grid, d_grid.p, sizeof(GridInfo), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return SPHB200_OK;
+    }
+    int push_ctl() {
+        CK(cudaMemcpyAsync(d_ctl.p, h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
+        return SPHB200_OK;
+    }
+    int set_time(double t, int64_t it) override {
+        CK(cudaSetDevice(device));
+        int rc = sync_ctl();
+        if (rc) return rc;
+        h_ctl->total_time = t;
+        h_ctl->iteration = it;
+        rc = push_ctl();
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(stream));
+        return SPHB200_OK;
+    }
+    void fill_report(sphb200_report *rep) {
+        if (!rep) return;
+        rep->iteration = h_ctl->iteration;
+        rep->index_counter = 0;
+        rep->n_rebuilds = h_ctl->n_rebuilds;
+        rep->n_particles = slab.active ? (int64_t)(h_grid->own_p1 - h_grid->own_p0) : n;
+        rep->n_halo = slab.active ? n - rep->n_particles : 0;
+        rep->total_time = h_ctl->total_time;
+        rep->current_dt = h_ctl->current_dt;
+        rep->delta_x = h_ctl->delta_x;
+    }
+    int get_report(sphb200_report *rep) override {
+        CK(cudaSetDevice(device));
+        int rc = sync_ctl();
+        if (rc) return rc;
+        fill_report(rep);
+        if (rep && have_cells) {
+            int64_t nc = 0;
+            rc = count_occupied(&nc);
+            if (rc) return rc;
+            rep->index_counter = nc + 1;   // IndexCounter counts the dummy first entry too, :145-160
+        }
+        return SPHB200_OK;
+    }
+
+    // ------------------------------------------------------------------ kernel launch helpers
+    Table<T, D> table(bool scratch) {
+        Table<T, D> t;
+        t.A = scratch ? A2.p : A.p;
+        t.B = scratch ? B2.p : B.p;
+        t.acc = scratch ? acc2.p : acc.p;
+        t.ghost = prm.mdbc ? (scratch ? ghost2.p : ghost.p) : nullptr;
+        t.id = scratch ? id2.p : id.p;
+        t.group = scratch ? group2.p : group.p;
+        t.type = scratch ? type2.p : type.p;
+        t.ckey = scratch ? ckey2.p : ckey.p;
+        return t;
+    }
+
+    // UpdateNeighbors! — every kernel is predicated on ctl->do_rebuild
+    int enqueue_rebuild() {
+        const int nn = (int)n;
+        const int gp = grid_for(nn);
+        const int gc = grid_for(cell_cap);
+        const int nscan = (int)(cell_cap / SCAN_CHUNK + 1);
+        k_cell_bbox<T, D><<<gp, 256, 0, stream>>>(A.p, nn, prm.H_inv, ccoord.p, d_ctl.p, d_grid.p);
+        k_grid_setup<D><<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, am, cell_cap, row_cap, own_lo, own_hi);
+        k_zero_counts<<<gc, 256, 0, stream>>>(d_ctl.p, d_grid.p, cell_count.p);
+        k_cell_count<D><<<gp, 256, 0, stream>>>(ccoord.p, nn, am, d_ctl.p, d_grid.p, key_tmp.p, slot_tmp.p, cell_count.p);
+        k_scan_partials<<<nscan, SCAN_THREADS, 0, stream>>>(d_ctl.p, d_grid.p, cell_count.p, scan_partial.p);
+        k_scan_top<<<1, 1024, 0, stream>>>(d_ctl.p, d_grid.p, scan_partial.p);
+        k_scan_final<<<nscan, SCAN_THREADS, 0, stream>>>(d_ctl.p, d_grid.p, cell_count.p, scan_partial.p, cell_start.p);
+        k_scatter_unstable<<<gp, 256, 0, stream>>>(d_ctl.p, key_tmp.p, slot_tmp.p, nn, cell_start.p, tmp_idx.p);
+        k_stable_rank<<<gp, 256, 0, stream>>>(d_ctl.p, key_tmp.p, tmp_idx.p, nn, cell_start.p, perm.p);
+        k_gather_table<T, D><<<gp, 256, 0, stream>>>(d_ctl.p, perm.p, nn, table(false), table(true), key_tmp.p);
+        k_copy_table<T, D><<<gp, 256, 0, stream>>>(d_ctl.p, nn, table(true), table(false));
+        k_build_bricks<<<1, 256, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, BT, bricks.p, brick_cap, nn);
+        k_finish_rebuild<<<1, 1, 0, stream>>>(d_ctl.p);
+        launches += 13;
+        CK(cudaGetLastError());
+        return SPHB200_OK;
+    }
+
+    template <int PASS, bool GEN, bool COMPACT>
+    int launch_interact_t(int epilogue) {
+        using SS = StageSizes<T, D, PASS, GEN>;
+        auto kern = k_interact<T, D, PASS, GEN, COMPACT, BT>;
+        const int list_bytes = COMPACT ? LIST_CAP * BT * 2 : 0;
+        int smem = std::min(opt_smem_kb, 200) * 1024;
+        int cap = ((smem - list_bytes - 64) / SS::per_candidate) & ~3;
+        cap = std::min(cap, 32764);
+        if (cap < 64) return fail(SPHB200_EINVAL, "shared-memory budget too small");
+        smem = cap * SS::per_candidate + list_bytes;
+        static int configured_smem = -1;   // per instantiation
+        if (configured_smem != smem) {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured_smem = smem;
+        }
+        static int ctas_per_sm = 0;
+        static int ctas_smem = -1;
+        if (ctas_smem != smem) {
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, BT, smem));
+            ctas_smem = smem;
+            if (ctas_per_sm < 1) return fail(SPHB200_ECUDA, "interaction kernel does not fit on an SM");
+        }
+        InteractArgs<T, D> g;
+        memset(&g, 0, sizeof g);
+        g.A = PASS ? Ah.p : A.p;
+        g.B = PASS ? Bh.p : B.p;
+        g.RN = RN.p;
+        g.Bn = B2.p;   // vₙ snapshot (LaminarSPS pass 2, Q2); B itself is rewritten by the fused corrector
+        g.An_rw = A.p;
+        g.Bn_rw = B.p;
+        g.Ah_out = Ah.p;
+        g.Bh_out = Bh.p;
+        g.drhodt = drhodt.p;
+        g.acc = acc.p;
+        g.gradC = gradC.p;
+        g.divr = divr.p;
+        g.ksum = ksum.p;
+        g.kgrad = kgrad.p;
+        g.cell_start = cell_start.p;
+        g.ckey = ckey.p;
+        g.type = type.p;
+        g.bricks = bricks.p;
+        g.grid = d_grid.p;
+        g.ctl = d_ctl.p;
+        g.phys = ph;
+        g.cap = cap;
+        g.epilogue = epilogue;
+        g.use_tma = opt_tma;
+        g.ref_major_is_s = ref_major_is_s;
+        g.counter_slot = PASS;
+        int blocks = num_sms * ctas_per_sm;
+        int64_t maxb = (n + BT - 1) / BT + (int64_t)row_cap;
+        if ((int64_t)blocks > maxb) blocks = (int)std::max<int64_t>(1, maxb);
+        kern<<<blocks, BT, smem, stream>>>(g);
+        ++launches;
+        CK(cudaGetLastError());
+        return SPHB200_OK;
+    }
+    int launch_interact(int pass, int epilogue) {
+        if (generic) return pass ? launch_interact_t<1, true, false>(epilogue) : launch_interact_t<0, true, false>(epilogue);
+        if (opt_compact) return pass ? launch_interact_t<1, false, true>(epilogue) : launch_interact_t<0, false, true>(epilogue);
+        return pass ? launch_interact_t<1, false, false>(epilogue) : launch_interact_t<0, false, false>(epilogue);
+    }
+
+    // state-n snapshots the pass-2 pair terms read (Q2): ρₙ always, vₙ for LaminarSPS
+    int enqueue_snapshots() {
+        k_snapshot_rho<T, D><<<grid_for(n), 256, 0, stream>>>(A.p, RN.p, (int)n, d_ctl.p);
+        ++launches;
+        CK(cudaGetLastError());
+        if (prm.viscosity == SPHB200_VISC_LAMINAR_SPS)
+            CK(cudaMemcpyAsync(B2.p, B.p, (size_t)n * sizeof(TB), cudaMemcpyDeviceToDevice, stream));
+        return SPHB200_OK;
+    }
+    int enqueue_mdbc() {
+        const int nn = (int)n;
+        k_mdbc_gather<T, D><<<grid_for(nn, 128), 128, 0, stream>>>(A.p, ghost.p, type.p, cell_start.p, d_grid.p, am, nn, ph,
+                                                                   prm.H_inv, rho_new.p, has_new.p, d_ctl.p);
+        k_mdbc_apply<T, D><<<grid_for(nn), 256, 0, stream>>>(A.p, RN.p, type.p, rho_new.p, has_new.p, nn, d_ctl.p);
+        launches += 2;
+        CK(cudaGetLastError());
+        return SPHB200_OK;
+    }
+    int enqueue_motion(double dt2) {
+        if (motions.n == 0) return SPHB200_OK;
+        k_progress_motion<T, D><<<grid_for(n), 256, 0, stream>>>(A.p, B.p, type.p, group.p, (int)n, motions, dt2, d_ctl.p);
+        ++launches;
+        CK(cudaGetLastError());
+        return SPHB200_OK;
+    }
+
+    // phase A of one step: S0, S1 and the S2 decision
+    int enqueue_step_head() {
+        const int nn = (int)n;
+        k_reduce_dt_dx<T, D><<<grid_for(nn), 256, 0, stream>>>(A.p, B.p, Ah.p, acc.p, 0, nn, ph.h, ph.eta2, have_half ? 1 : 0,
+                                                               d_ctl.p);
+        int rc = slab.allreduce_ctl(this, d_ctl.p, stream);
+        if (rc) return rc;
+        k_step_control<T><<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, ph.h, ph.c0, (T)prm.cfl);
+        launches += 2;
+        CK(cudaGetLastError());
+        return SPHB200_OK;
+    }
+    // phase B: S2 .. S19
+    int enqueue_step_body() {
+        int rc;
+        if ((rc = enqueue_rebuild())) return rc;
+        if ((rc = enqueue_motion(-1.0))) return rc;                       // S3
+        if ((rc = enqueue_snapshots())) return rc;
+        if (prm.mdbc && (rc = enqueue_mdbc())) return rc;                 // S6
+        if ((rc = launch_interact(0, EPI_FUSED))) return rc;              // S4-S10, S13
+        if ((rc = enqueue_motion(-1.0))) return rc;                       // S12
+        if ((rc = launch_interact(1, EPI_FUSED))) return rc;              // S11, S14-S18
+        k_step_end<<<1, 1, 0, stream>>>(d_ctl.p);                         // S19
+        ++launches;
+        CK(cudaGetLastError());
+        have_half = true;
+        have_cells = true;
+        return SPHB200_OK;
+    }
+
+    // grow the dense cell grid after an ECAPACITY stop; returns OK if the step can be resumed
+    int recover_capacity() {
+        long long need = 1;
+        for (int k = 0; k < D; ++k) need *= ((long long)h_grid->bb_max[k] - h_grid->bb_min[k] + 3);
+        if (need <= 0 || need > (1ll << 28)) return fail(SPHB200_ECAPACITY, "particles left the tractable domain (dense cell grid would need %lld cells)", need);
+        int rc = alloc_cells(2 * need + 1024);
+        if (rc) return rc;
+        h_ctl->error = 0;
+        return push_ctl();
+    }
+
+    int run_steps(int64_t nsteps, bool until_target) {
+        if (!uploaded) return fail(SPHB200_ESTATE, "step before upload");
+        CK(cudaSetDevice(device));
+        if (slab.active) return run_steps_slab(nsteps, until_target);
+        int64_t done_steps = 0;
+        int rc = sync_ctl();
+        if (rc) return rc;
+        const int64_t it0 = h_ctl->iteration;
+        while (until_target || done_steps < nsteps) {
+            int64_t batch = opt_batch;
+            if (!until_target) batch = std::min<int64_t>(batch, nsteps - done_steps);
+            else if (h_ctl->current_dt > 0.0) {
+                double rem = (h_ctl->target_time - h_ctl->total_time) / h_ctl->current_dt;
+                batch = std::max<int64_t>(1, std::min<int64_t>(batch, (int64_t)(rem * 1.02) + 2));
+            } else {
+                batch = 1;
+            }
+            for (int64_t s = 0; s < batch; ++s) {
+                if ((rc = enqueue_step_head())) return rc;
+                if ((rc = enqueue_step_body())) return rc;
+            }
+            if ((rc = sync_ctl())) return rc;
+            while (h_ctl->error == SPHB200_ECAPACITY) {
+                if ((rc = recover_capacity())) return rc;
+                if (h_ctl->step_open && (rc = enqueue_step_body())) return rc;
+                if ((rc = sync_ctl())) return rc;
+            }
+            if (h_ctl->error == SPHB200_ENUMERIC)
+                return fail(SPHB200_ENUMERIC, "non-finite state or time step at iteration %lld (t = %g)", h_ctl->iteration, h_ctl->total_time);
+            if (h_ctl->error) return fail(h_ctl->error, "device reported error %d", h_ctl->error);
+            done_steps = h_ctl->iteration - it0;
+            if (until_target && h_ctl->done) break;
+        }
+        return SPHB200_OK;
+    }
+    int run_steps_slab(int64_t nsteps, bool until_target);
+
+    int step(int64_t nsteps, int reset_dx, sphb200_report *rep) override {
+        if (!uploaded) return fail(SPHB200_ESTATE, "step before upload");
+        CK(cudaSetDevice(device));
+        if (nsteps < 0) return fail(SPHB200_EINVAL, "negative step count");
+        if (reset_dx || !have_cells) {
+            int rc = sync_ctl();
+            if (rc) return rc;
+            h_ctl->delta_x = (double)(T(1) + ph.h);   // src/SPHCellList.jl:739
+            h_ctl->use_target = 0;
+            h_ctl->done = 0;
+            if ((rc = push_ctl())) return rc;
+        }
+        int rc = run_steps(nsteps, false);
+        if (rc) return rc;
+        fill_report(rep);
+        return SPHB200_OK;
+    }
+    int simulation_loop(double t_next, sphb200_report *rep) override {
+        if (!uploaded) return fail(SPHB200_ESTATE, "simulation_loop before upload");
+        CK(cudaSetDevice(device));
+        int rc = sync_ctl();
+        if (rc) return rc;
+        h_ctl->delta_x = (double)(T(1) + ph.h);
+        h_ctl->use_target = 1;
+        h_ctl->target_time = t_next;
+        h_ctl->done = 0;
+        if ((rc = push_ctl())) return rc;
+        rc = run_steps(0, true);
+        h_ctl->use_target = 0;
+        h_ctl->done = 0;
+        int rc2 = push_ctl();
+        cudaStreamSynchronize(stream);
+        if (rc) return rc;
+        if (rc2) return rc2;
+        fill_report(rep);
+        return SPHB200_OK;
+    }
+
+    // ------------------------------------------------------------------ stage-level entry points
+    int force_flag_rebuild() {
+        int rc = sync_ctl();
+        if (rc) return rc;
+        h_ctl->do_rebuild = 1;
+        h_ctl->done = 0;
+        if ((rc = push_ctl())) return rc;
+        for (int k = 0; k < 3; ++k) {
+            h_grid->bb_min[k] = INT_MAX;
+            h_grid->bb_max[k] = INT_MIN;
+        }
+        CK(cudaMemcpyAsync(d_grid.p, h_grid, sizeof(GridInfo), cudaMemcpyHostToDevice, stream));
+        return SPHB200_OK;
+    }
+    int update_neighbors(int64_t *index_counter) override {
+        if (!uploaded) return fail(SPHB200_ESTATE, "update_neighbors before upload");
+        CK(cudaSetDevice(device));
+        if (slab.active) return fail(SPHB200_ESTATE, "stage-level calls are single-GPU only");
+        int rc;
+        for (int attempt = 0; attempt < 3; ++attempt) {
+            if ((rc = force_flag_rebuild())) return rc;
+            if ((rc = enqueue_rebuild())) return rc;
+            if ((rc = sync_ctl())) return rc;
+            if (h_ctl->error != SPHB200_ECAPACITY) break;
+            if ((rc = recover_capacity())) return rc;
+        }
+        if (h_ctl->error) return fail(h_ctl->error, "update_neighbors: device reported error %d", h_ctl->error);
+        have_cells = true;
+        if (index_counter) {
+            int64_t nc = 0;
+            if ((rc = count_occupied(&nc))) return rc;
+            *index_counter = nc + 1;
+        }
+        return SPHB200_OK;
+    }
+    int fetch_cell_start(std::vector<int> &cs) {
+        cs.resize((size_t)h_grid->ncell + 1);
+        CK(cudaMemcpyAsync(cs.data(), cell_start.p, cs.size() * 4, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return SPHB200_OK;
+    }
+    int count_occupied(int64_t *out) {
+        std::vector<int> cs;
+        int rc = sync_ctl();
+        if (rc) return rc;
+        if ((rc = fetch_cell_start(cs))) return rc;
+        int64_t nc = 0;
+        for (int c = 0; c < h_grid->ncell; ++c) nc += cs[c + 1] > cs[c];
+        *out = nc;
+        return SPHB200_OK;
+    }
+    int get_cell_list(int64_t *n_cells, int64_t *cells, int64_t *start) override {
+        if (!have_cells) return fail(SPHB200_ESTATE, "get_cell_list before update_neighbors");
+        CK(cudaSetDevice(device));
+        std::vector<int> cs;
+        int rc = sync_ctl();
+        if (rc) return rc;
+        if ((rc = fetch_cell_start(cs))) return rc;
+        // occupied cells in the REFERENCE's order (last dimension most significant)
+        struct Occ { int c[3]; int s, e; };
+        std::vector<Occ> occ;
+        for (int key = 0; key < h_grid->ncell; ++key)
+            if (cs[key + 1] > cs[key]) {
+                Occ o;
+                o.c[0] = o.c[1] = o.c[2] = 0;
+                key_to_cell(key, o.c);
+                o.s = cs[key];
+                o.e = cs[key + 1];
+                occ.push_back(o);
+            }
+        if (!ref_major_is_s)
+            std::stable_sort(occ.begin(), occ.end(), [](const Occ &a, const Occ &b) {
+                for (int k = D - 1; k >= 0; --k)
+                    if (a.c[k] != b.c[k]) return a.c[k] < b.c[k];
+                return false;
+            });
+        if (n_cells) *n_cells = (int64_t)occ.size();
+        if (cells)
+            for (size_t k = 0; k < occ.size(); ++k)
+                for (int d = 0; d < D; ++d) cells[k * D + d] = occ[k].c[d];
+        if (start) {
+            for (size_t k = 0; k < occ.size(); ++k) start[k] = occ[k].s;
+            start[occ.size()] = occ.empty() ? 0 : occ.back().e;
+        }
+        return SPHB200_OK;
+    }
+    int pressure(int half) override {
+        if (!uploaded) return fail(SPHB200_ESTATE, "pressure before upload");
+        CK(cudaSetDevice(device));
+        k_pressure<T, D><<<grid_for(n), 256, 0, stream>>>(half ? Ah.p : A.p, half ? Bh.p : B.p, (int)n, ph, d_ctl.p);
+        ++launches;
+        CK(cudaGetLastError());
+        return SPHB200_OK;
+    }
+    int neighbor_loop(int pass, void *drhodt_out, void *acc_out) override {
+        if (!have_cells) return fail(SPHB200_ESTATE, "neighbor_loop before update_neighbors");
+        if (pass && !have_half) return fail(SPHB200_ESTATE, "neighbor_loop(pass 1) before half_time_step");
+        CK(cudaSetDevice(device));
+        k_reset_counters<<<1, 1, 0, stream>>>(d_ctl.p);
+        ++launches;
+        int rc;
+        if (!pass) {
+            if ((rc = enqueue_snapshots())) return rc;
+        }
+        if ((rc = launch_interact(pass ? 1 : 0, EPI_STORE))) return rc;
+        if (drhodt_out) CK(cudaMemcpyAsync(drhodt_out, drhodt.p, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        if (acc_out) {
+            T *d_tmp = (T *)stage.p;
+            k_unpack_vec<T, D><<<grid_for(n), 256, 0, stream>>>((int)n, acc.p, d_tmp);
+            ++launches;
+            CK(cudaMemcpyAsync(acc_out, d_tmp, (size_t)n * D * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        }
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaGetLastError());
+        return SPHB200_OK;
+    }
+    int delta_t(double *dt) override {
+        if (!uploaded) return fail(SPHB200_ESTATE, "delta_t before upload");
+        CK(cudaSetDevice(device));
+        int rc = sync_ctl();
+        if (rc) return rc;
+        h_ctl->red_disp2 = h_ctl->red_visc = h_ctl->red_acc2 = 0ull;
+        if ((rc = push_ctl())) return rc;
+        k_reduce_dt_dx<T, D><<<grid_for(n), 256, 0, stream>>>(A.p, B.p, Ah.p, acc.p, 0, (int)n, ph.h, ph.eta2, 0, d_ctl.p);
+        ++launches;
+        if ((rc = sync_ctl())) return rc;
+        T visc = (T)bits_to_double_host(h_ctl->red_visc);
+        T acc2 = (T)bits_to_double_host(h_ctl->red_acc2);
+        T dt1 = sph_sqrt(ph.h / sph_sqrt(acc2));
+        T dt2 = ph.h / (ph.c0 + visc);
+        if (dt) *dt = (double)((T)prm.cfl * std::min(dt1, dt2));
+        h_ctl->red_disp2 = h_ctl->red_visc = h_ctl->red_acc2 = 0ull;
+        if ((rc = push_ctl())) return rc;
+        CK(cudaStreamSynchronize(stream));
+        return SPHB200_OK;
+    }
+    static double bits_to_double_host(unsigned long long b) {
+        double d;
+        memcpy(&d, &b, 8);
+        return d;
+    }
+    int progress_motion(double dt2) override {
+        if (!uploaded) return fail(SPHB200_ESTATE, "progress_motion before upload");
+        CK(cudaSetDevice(device));
+        return enqueue_motion(dt2);
+    }
+    int apply_mdbc() override {
+        if (!prm.mdbc) return SPHB200_OK;   // NoMDBC: no-op method, src/SPHCellList.jl:486-489
+        if (!have_cells) return fail(SPHB200_ESTATE, "apply_mdbc before update_neighbors");
+        CK(cudaSetDevice(device));
+        int rc;
+        if ((rc = enqueue_snapshots())) return rc;
+        return enqueue_mdbc();
+    }
+    int half_time_step(double dt2) override {
+        if (!uploaded) return fail(SPHB200_ESTATE, "half_time_step before upload");
+        CK(cudaSetDevice(device));
+        k_half_step<T, D><<<grid_for(n), 256, 0, stream>>>(A.p, B.p, acc.p, drhodt.p, type.p, Ah.p, Bh.p, 0, (int)n, ph, dt2, d_ctl.p);
+        ++launches;
+        CK(cudaGetLastError());
+        have_half = true;
+        return SPHB200_OK;
+    }
+    int full_time_step(double dt) override {
+        if (!have_half) return fail(SPHB200_ESTATE, "full_time_step before half_time_step");
+        CK(cudaSetDevice(device));
+        k_full_step<T, D><<<grid_for(n), 256, 0, stream>>>(A.p, B.p, acc.p, drhodt.p, Ah.p, type.p, gradC.p, divr.p, 0, (int)n, ph,
+                                                           dt, d_ctl.p);
+        ++launches;
+        CK(cudaGetLastError());
+        return SPHB200_OK;
+    }
+    int download_half(void *pos_h, void *vel_h, void *rho_h, void *press_h) override {
+        if (!have_half) return fail(SPHB200_ESTATE, "download_half before half_time_step");
+        CK(cudaSetDevice(device));
+        unsigned char *sp = stage.p;
+        size_t vb = (size_t)n * D * sizeof(T), sb = (size_t)n * sizeof(T);
+        T *d_pos = (T *)sp; sp += vb;
+        T *d_vel = (T *)sp; sp += vb;
+        T *d_rho = (T *)sp; sp += sb;
+        T *d_pr = (T *)sp; sp += sb;
+        k_unpack_download<T, D><<<grid_for(n), 256, 0, stream>>>((int)n, Ah.p, Bh.p, nullptr, d_pos, d_vel, nullptr, d_rho, d_pr);
+        ++launches;
+        if (pos_h) CK(cudaMemcpyAsync(pos_h, d_pos, vb, cudaMemcpyDeviceToHost, stream));
+        if (vel_h) CK(cudaMemcpyAsync(vel_h, d_vel, vb, cudaMemcpyDeviceToHost, stream));
+        if (rho_h) CK(cudaMemcpyAsync(rho_h, d_rho, sb, cudaMemcpyDeviceToHost, stream));
+        if (press_h) CK(cudaMemcpyAsync(press_h, d_pr, sb, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return SPHB200_OK;
+    }
+    int download_aux(void *gradc_out, void *divr_out, void *ksum_out, void *kgrad_out) override {
+        if (!uploaded) return fail(SPHB200_ESTATE, "download_aux before upload");
+        CK(cudaSetDevice(device));
+        T *d_tmp = (T *)stage.p;
+        size_t vb = (size_t)n * D * sizeof(T), sb = (size_t)n * sizeof(T);
+        if (gradc_out) {
+            if (!prm.shifting) return fail(SPHB200_EINVAL, "gradC requires PlanarShifting");
+            k_unpack_vec<T, D><<<grid_for(n), 256, 0, stream>>>((int)n, gradC.p, d_tmp);
+            ++launches;
+            CK(cudaMemcpyAsync(gradc_out, d_tmp, vb, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+        }
+        if (divr_out) {
+            if (!prm.shifting) return fail(SPHB200_EINVAL, "div r requires PlanarShifting");
+            CK(cudaMemcpyAsync(divr_out, divr.p, sb, cudaMemcpyDeviceToHost, stream));
+        }
+        if (ksum_out) {
+            if (!prm.kernel_output) return fail(SPHB200_EINVAL, "kernel sums require StoreKernelOutput");
+            CK(cudaMemcpyAsync(ksum_out, ksum.p, sb, cudaMemcpyDeviceToHost, stream));
+        }
+        if (kgrad_out) {
+            if (!prm.kernel_output) return fail(SPHB200_EINVAL, "kernel gradient sums require StoreKernelOutput");
+            k_unpack_vec<T, D><<<grid_for(n), 256, 0, stream>>>((int)n, kgrad.p, d_tmp);
+            ++launches;
+            CK(cudaMemcpyAsync(kgrad_out, d_tmp, vb, cudaMemcpyDeviceToHost, stream));
+        }
+        CK(cudaStreamSynchronize(stream));
+        return SPHB200_OK;
+    }
+
+    // per-stage device times of one step (ms): reduce+control, rebuild, pass 0, pass 1 — the
+    // reference's TimerOutputs labels "01", "02", "05/06", "08-11" (src/SPHCellList.jl:748-800)
+    int stage_times(double *ms_out, int cnt) override {
+        if (!uploaded || !have_cells) return fail(SPHB200_ESTATE, "stage_times needs a running simulation");
+        CK(cudaSetDevice(device));
+        cudaEvent_t ev[6];
+        for (auto &e : ev) CK(cudaEventCreate(&e));
+        int rc = 0;
+        CK(cudaEventRecord(ev[0], stream));
+        if ((rc = enqueue_step_head())) return rc;
+        CK(cudaEventRecord(ev[1], stream));
+        if ((rc = enqueue_rebuild())) return rc;
+        if ((rc = enqueue_motion(-1.0))) return rc;
+        if ((rc = enqueue_snapshots())) return rc;
+        if (prm.mdbc && (rc = enqueue_mdbc())) return rc;
+        CK(cudaEventRecord(ev[2], stream));
+        if ((rc = launch_interact(0, EPI_FUSED))) return rc;
+        CK(cudaEventRecord(ev[3], stream));
+        if ((rc = enqueue_motion(-1.0))) return rc;
+        if ((rc = launch_interact(1, EPI_FUSED))) return rc;
+        CK(cudaEventRecord(ev[4], stream));
+        k_step_end<<<1, 1, 0, stream>>>(d_ctl.p);
+        ++launches;
+        CK(cudaEventRecord(ev[5], stream));
+        CK(cudaStreamSynchronize(stream));
+        have_half = true;
+        for (int k = 0; k < 5 && k < cnt; ++k) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+            ms_out[k] = ms;
+        }
+        for (auto &e : ev) cudaEventDestroy(e);
+        if ((rc = sync_ctl())) return rc;
+        if (h_ctl->error) return fail(h_ctl->error, "device reported error %d", h_ctl->error);
+        return SPHB200_OK;
+    }
+
+    // ------------------------------------------------------------------ slabs (sph_slab.cuh)
+    int comm_init(const uint8_t *uid, int rank, int world, int axis) override;
+    int set_slab(int64_t lo, int64_t hi) override;
+    int column_histogram(int axis, int64_t *cell_min, int64_t *n_columns, int64_t *counts, int64_t cap) override;
+#undef CK
+};
+
+}  // namespace
+
+#include "sph_slab_impl.cuh"
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+extern "C" {
+
+int sphb200_abi_version(void) { return SPHB200_ABI_VERSION; }
+
+int sphb200_create(const sphb200_params *p, int device, sphb200_sim **out) {
+    if (!p || !out) {
+        g_create_error = "sphb200_create: null argument";
+        return SPHB200_EINVAL;
+    }
+    *out = nullptr;
+    if (p->abi_version != SPHB200_ABI_VERSION) {
+        g_create_error = "sphb200_create: ABI version mismatch";
+        return SPHB200_EINVAL;
+    }
+    if ((p->dim != 2 && p->dim != 3) || (p->real_bytes != 4 && p->real_bytes != 8)) {
+        g_create_error = "sphb200_create: dim must be 2 or 3 and real_bytes 4 or 8";
+        return SPHB200_EINVAL;
+    }
+    if (!(p->h > 0.0) || !(p->H > 0.0) || !(p->rho0 > 0.0) || !(p->m0 > 0.0) || !(p->c0 > 0.0) || !(p->cfl > 0.0) ||
+        p->n_motions < 0 || p->n_motions > SPHB200_MAX_MOTIONS || p->kernel < 0 || p->kernel > 1 || p->viscosity < 0 ||
+        p->viscosity > 3 || p->diffusion < 0 || p->diffusion > 3) {
+        g_create_error = "sphb200_create: invalid constants or model selectors";
+        return SPHB200_EINVAL;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1) {
+        g_create_error = std::string("sphb200_create: no CUDA device available (") + cudaGetErrorString(e) +
+                         "); libsphb200 has no CPU fallback";
+        return SPHB200_ECUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "sphb200_create: device index out of range";
+        return SPHB200_EINVAL;
+    }
+    sphb200_sim *s = nullptr;
+    int rc = SPHB200_OK;
+    if (p->dim == 2 && p->real_bytes == 8) { auto *q = new Sim<double, 2>(*p, device); rc = q->init(); s = q; }
+    else if (p->dim == 2) { auto *q = new Sim<float, 2>(*p, device); rc = q->init(); s = q; }
+    else if (p->real_bytes == 8) { auto *q = new Sim<double, 3>(*p, device); rc = q->init(); s = q; }
+    else { auto *q = new Sim<float, 3>(*p, device); rc = q->init(); s = q; }
+    if (rc != SPHB200_OK) {
+        g_create_error = s->err;
+        delete s;
+        return rc;
+    }
+    *out = s;
+    return SPHB200_OK;
+}
+
+int sphb200_destroy(sphb200_sim *sim) {
+    delete sim;
+    return SPHB200_OK;
+}
+const char *sphb200_last_error(const sphb200_sim *sim) { return sim ? sim->err.c_str() : g_create_error.c_str(); }
+
+#define NEED(s)  \
+    if (!(s)) return SPHB200_EINVAL
+
+int sphb200_upload(sphb200_sim *s, int64_t n, const void *pos, const void *vel, const void *acc, const void *rho,
+                   const uint8_t *type, const uint64_t *group, const int64_t *id, const void *gp, const void *gn) {
+    NEED(s);
+    return s->upload(n, pos, vel, acc, rho, type, group, id, gp, gn);
+}
+int sphb200_download(sphb200_sim *s, int order, void *pos, void *vel, void *acc, void *rho, void *press, int64_t *id,
+                     uint8_t *type, uint64_t *group, int64_t *cells) {
+    NEED(s);
+    return s->download(order, pos, vel, acc, rho, press, id, type, group, cells);
+}
+int64_t sphb200_num_particles(const sphb200_sim *s) { return s ? s->num_particles() : 0; }
+int sphb200_set_time(sphb200_sim *s, double t, int64_t it) { NEED(s); return s->set_time(t, it); }
+int sphb200_simulation_loop(sphb200_sim *s, double t, sphb200_report *r) { NEED(s); return s->simulation_loop(t, r); }
+int sphb200_step(sphb200_sim *s, int64_t n, int reset, sphb200_report *r) { NEED(s); return s->step(n, reset, r); }
+int sphb200_get_report(sphb200_sim *s, sphb200_report *r) { NEED(s); return s->get_report(r); }
+int64_t sphb200_launch_count(const sphb200_sim *s) { return s ? s->launch_count() : 0; }
+int sphb200_update_neighbors(sphb200_sim *s, int64_t *ic) { NEED(s); return s->update_neighbors(ic); }
+int sphb200_get_cell_list(sphb200_sim *s, int64_t *nc, int64_t *cells, int64_t *start) { NEED(s); return s->get_cell_list(nc, cells, start); }
+int sphb200_pressure(sphb200_sim *s, int half) { NEED(s); return s->pressure(half); }
+int sphb200_neighbor_loop(sphb200_sim *s, int pass, void *d, void *a) { NEED(s); return s->neighbor_loop(pass, d, a); }
+int sphb200_delta_t(sphb200_sim *s, double *dt) { NEED(s); return s->delta_t(dt); }
+int sphb200_progress_motion(sphb200_sim *s, double dt2) { NEED(s); return s->progress_motion(dt2); }
+int sphb200_apply_mdbc(sphb200_sim *s) { NEED(s); return s->apply_mdbc(); }
+int sphb200_half_time_step(sphb200_sim *s, double dt2) { NEED(s); return s->half_time_step(dt2); }
+int sphb200_full_time_step(sphb200_sim *s, double dt) { NEED(s); return s->full_time_step(dt); }
+int sphb200_download_half(sphb200_sim *s, void *p, void *v, void *r, void *pr) { NEED(s); return s->download_half(p, v, r, pr); }
+int sphb200_download_aux(sphb200_sim *s, void *g, void *d, void *k, void *kg) { NEED(s); return s->download_aux(g, d, k, kg); }
+int sphb200_set_stream(sphb200_sim *s, void *stream) { NEED(s); return s->set_stream(stream); }
+int sphb200_set_option(sphb200_sim *s, const char *name, double value) { NEED(s); return s->set_option(name, value); }
+int sphb200_stage_times(sphb200_sim *s, double *ms, int n) { NEED(s); return s->stage_times(ms, n); }
+int sphb200_comm_unique_id(uint8_t id_out[128]) { return slab_unique_id(id_out); }
+int sphb200_comm_init(sphb200_sim *s, const uint8_t id[128], int rank, int world, int axis) { NEED(s); return s->comm_init(id, rank, world, axis); }
+int sphb200_set_slab(sphb200_sim *s, int64_t lo, int64_t hi) { NEED(s); return s->set_slab(lo, hi); }
+int sphb200_column_histogram(sphb200_sim *s, int axis, int64_t *cmin, int64_t *ncol, int64_t *counts, int64_t cap) {
+    NEED(s);
+    return s->column_histogram(axis, cmin, ncol, counts, cap);
+}
+}
