@@ -20,6 +20,8 @@
 // including its misses between rebuilds — hence the per-lane window test.
 #pragma once
 
+#include <type_traits>
+
 #include "sph_device.cuh"
 
 namespace sph {
@@ -154,6 +156,9 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
         // ---- this thread's target particle ------------------------------------------------
         const int i = br.t0 + tid;
         const bool valid = i < br.t1;
+        const int warp_first = br.t0 + (tid & ~31);
+        const bool warp_has_work = warp_first < br.t1;
+        const int last_lane = min(31, br.t1 - warp_first - 1) & 31;
         T xa[D], va[D], rho_a = T(1), P_a = T(0), rhon_a = T(1), ml_a = T(0);
         int cxi = cx0, cs_a = 0, ce_a = 0;
 #pragma unroll
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
         T drho = T(0), acc[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) acc[k] = T(0);
-        int cnt = 0;   // entries in this thread's list (COMPACT)
+        const FastTarget<T> ft = make_fast_target<T>(ph, rho_a, P_a, rhon_a, ml_a, PASS == 0);   // !GENERIC only
 
         // pair body for one staged candidate (smem slot sj), shared by both phases
         auto pair_body = [&](int sj, bool a_is_i) {
@@ -207,8 +212,7 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
                 r2 += xab[k] * xab[k];
             }
             if (!GENERIC) {
-                pair_fast<T, D>(ph, xab, r2, va, vb, rho_a, rho_b, P_a, P_b, rhon_a, rhon_b, ml_a * ml_b, a_is_i,
-                                drho, acc);
+                pair_fast<T, D, PASS == 0>(ph, ft, xab, r2, va, vb, rho_b, P_b, rhon_b, rsb > T(0), a_is_i, drho, acc);
             } else {
                 PairSide<T, D> sb;
 #pragma unroll
@@ -227,8 +231,13 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
                 pair_generic<T, D>(ph, sa, sb, xab, r2, a_is_i, sacc);
             }
         };
+        // per-thread list: slist[k * BT + tid]; waddr = shared address of the next free entry
+        const uint32_t waddr0 = smem_u32(slist + tid);
+        const uint32_t waddr_full = waddr0 + (uint32_t)((LIST_CAP - 4) * BT * 2);   // > : fewer than 4 free
+        uint32_t waddr = waddr0;
         auto flush = [&]() {
             if (COMPACT) {
+                const int cnt = (int)((waddr - waddr0) / (uint32_t)(BT * 2));
                 int m = warp_max(cnt);
                 for (int k = 0; k < m; ++k) {
                     if (k < cnt) {
@@ -236,7 +245,7 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
                         pair_body((int)(e & (ROLE_BIT - 1)), (e & ROLE_BIT) != 0);
                     }
                 }
-                cnt = 0;
+                waddr = waddr0;
             }
         };
 
@@ -305,17 +314,31 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
                 // staged global index range of this row in this stage
                 const int jbase = s_w0a[r] - s_off[r];   // global j = staged position + jbase
                 int jb = lo_s + jbase, je = hi_s + jbase;
-                // clip to the union of the warp's lane windows (windows are monotone in i)
-                int ulo = warp_min(valid ? lo : INT_MAX);
-                int uhi = warp_max(valid ? hi : INT_MIN);
-                jb = max(jb, ulo);
-                je = min(je, uhi);
+                // clip to the union of the warp's lane windows (windows are monotone in i), then
+                // widen to multiples of 4: the staged piece is 4-aligned at both ends and the
+                // per-lane window test rejects the extra candidates, so the unrolled body needs
+                // no bounds checks
+                // (lane windows are monotone in i and the valid lanes are a prefix of the warp:
+                //  the union is [lo of lane 0, hi of the last valid lane))
+                int ulo = __shfl_sync(0xffffffffu, lo, 0);
+                int uhi = __shfl_sync(0xffffffffu, hi, last_lane);
+                if (!warp_has_work) {
+                    ulo = INT_MAX;
+                    uhi = INT_MIN;
+                }
+                jb = max(jb, ulo) & ~3;
+                je = (min(je, uhi) + 3) & ~3;
                 const int sbase = -jbase - s0;          // smem slot = j + sbase
-                for (int j4 = jb; j4 < je; j4 += 4) {
+                const unsigned wlen = (unsigned)(hi - lo);
+                const T H2 = ph.H2;
+                auto cull = [&](auto same_row) {
+                    constexpr bool SAME_ROW = decltype(same_row)::value;
+                    const unsigned role_const = rowrole > 0 ? (unsigned)ROLE_BIT : 0u;
+                    const unsigned self_off = (unsigned)(i - cs_a);
+                    for (int j4 = jb; j4 < je; j4 += 4) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int j = j4 + u;
-                        if (j < je) {
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = j4 + u;
                             const int sj = j + sbase;
                             T xb[D];
                             L::pos(sA[sj], xb);
@@ -325,22 +348,38 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
                                 T dlt = xa[k] - xb[k];
                                 r2 += dlt * dlt;
                             }
-                            bool ok = (j >= lo) & (j < hi) & (r2 <= ph.H2) & (j != i);
-                            if (ok) {
-                                bool a_is_i = rowrole > 0 || (rowrole == 0 && ((j < cs_a) || (j > i && j < ce_a)));
-                                if (COMPACT) {
-                                    slist[cnt * BT + tid] = (unsigned short)(sj | (a_is_i ? ROLE_BIT : 0));
-                                    ++cnt;
-                                } else {
-                                    pair_body(sj, a_is_i);
-                                }
+                            // lane window [lo, hi) in one unsigned compare; the self pair is let
+                            // through on the fast path (it contributes exact zeros) and rejected
+                            // where a term is non-zero at r = 0 (kernel sums of the generic path)
+                            bool ok = (r2 <= H2) & ((unsigned)(j - lo) < wlen);
+                            if (GENERIC) ok &= (j != i);
+                            // role bit: constant per row, except in the target's own
+                            // row where a is "i" iff b's cell is lower, or same cell and a < b:
+                            //   j in [lo, cs_a) or (i, ce_a)  <=>  j < ce_a and not cs_a <= j <= i
+                            unsigned code = (unsigned)(j + (sbase + (int)role_const));
+                            if (SAME_ROW)
+                                code = (unsigned)sj | (((j < ce_a) & ((unsigned)(j - cs_a) > self_off)) ? (unsigned)ROLE_BIT : 0u);
+                            if (COMPACT) {
+                                // predicated append (no branch): store + pointer bump under `ok`
+                                asm volatile(
+                                    "{\n\t.reg .pred p;\n\t"
+                                    "setp.ne.u32 p, %2, 0;\n\t"
+                                    "@p st.shared.u16 [%0], %1;\n\t"
+                                    "@p add.u32 %0, %0, %3;\n\t}"
+                                    : "+r"(waddr)
+                                    : "h"((unsigned short)code), "r"((unsigned)ok), "n"(BT * 2)
+                                    : "memory");
+                            } else if (ok) {
+                                pair_body(sj, (code & ROLE_BIT) != 0);
                             }
                         }
+                        if (COMPACT) {
+                            if (__any_sync(0xffffffffu, waddr > waddr_full)) flush();
+                        }
                     }
-                    if (COMPACT) {
-                        if (__any_sync(0xffffffffu, cnt > LIST_CAP - 4)) flush();
-                    }
-                }
+                };
+                if (rowrole == 0) cull(std::true_type{});
+                else cull(std::false_type{});
             }
             flush();
             __syncthreads();   // everyone is done with this stage's shared memory

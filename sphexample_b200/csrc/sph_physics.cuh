@@ -35,6 +35,7 @@ struct Phys {
     T ddt_lin;   // rho0 * g * rho0 / (cb * gamma)  ρᴴ = ddt_lin * z_ab, :113-122
     T eos_b;     // c0^2 rho0 / 7                  src/SimulationEquations.jl:9-11
     T w_dx;      // W(dx) for the tensile correction, src/SPHKernels.jl:120-126
+    T visc_k2;   // 2 m0 alpha c0 h : Π coefficient with 1/ρ̄ = 2/(ρ_a+ρ_b), src/SPHViscosityModels.jl:66-70
     int kernel, viscosity, diffusion, shifting, kernel_output, mdbc;
 };
 
@@ -42,6 +43,27 @@ template <class T> SPH_HD T sph_sqrt(T x) { return sqrt(x); }
 template <> SPH_HD float sph_sqrt<float>(float x) { return sqrtf(x); }
 template <class T> SPH_HD T sph_abs(T x) { return fabs(x); }
 template <> SPH_HD float sph_abs<float>(float x) { return fabsf(x); }
+// reciprocal / square root of the fast pair body: IEEE on the host and in fp64, MUFU in fp32
+template <class T> SPH_HD T sph_rcp(T x) { return T(1) / x; }
+template <> SPH_HD float sph_rcp<float>(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+template <class T> SPH_HD T sph_sqrt_fast(T x) { return sqrt(x); }
+template <> SPH_HD float sph_sqrt_fast<float>(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
 template <class T> SPH_HD T sph_min(T a, T b) { return a < b ? a : b; }
 template <class T> SPH_HD T sph_max(T a, T b) { return a > b ? a : b; }
 
@@ -128,37 +150,58 @@ SPH_HD void accum_zero(PairAccum<T, D> &s) {
 // output — the model set of every BASELINE config (example/Dambreak3d.jl:57-59 etc.).
 // xab / r2 are passed in because the caller has just computed them for the cut-off test.
 // ---------------------------------------------------------------------------------------------
-template <class T, int D>
-SPH_HD void pair_fast(const Phys<T> &p, const T *xab, T r2, const T *va, const T *vb, T rho_a, T rho_b,
-                      T P_a, T P_b, T rhon_a, T rhon_b, T mlab, bool a_is_i, T &drho, T *acc) {
-    T d = sph_sqrt(sph_abs(r2));
-    T q = sph_min(sph_max(d * p.h_inv, T(0)), T(2));
-    T qm2 = q - T(2);
-    T fac = p.gradw_c * (qm2 * qm2 * qm2);          // ∇W = fac * x_ab
-    T vab[D];
+// Per-target constants of the fast pair body (computed once per particle, not per pair).
+template <class T>
+struct FastTarget {
+    T P, rhon, inv_rhon;   // P_a, ρₙ_a, 1/ρₙ_a
+    T c_cont;              //  ρ_a m0                    continuity prefactor
+    T c_ddt;               // −2 δφ h c0 m0 ML_a         diffusion prefactor
+    T c_pres;              // −m0 / ρ_a                  pressure prefactor
+};
+template <class T>
+SPH_HD FastTarget<T> make_fast_target(const Phys<T> &p, T rho, T P, T rhon, T ml, bool same_rho) {
+    FastTarget<T> f;
+    f.P = P;
+    f.rhon = rhon;
+    T inv_rho = sph_rcp(rho);
+    f.inv_rhon = same_rho ? inv_rho : sph_rcp(rhon);
+    f.c_cont = rho * p.m0;
+    f.c_ddt = T(-2) * p.ddt_k * p.m0 * ml;
+    f.c_pres = -p.m0 * inv_rho;
+    return f;
+}
+
+// SAME_RHO: the pass density is the state-n density (pass 1 of the step), so 1/ρ_b serves both
+// the continuity/pressure terms and the diffusion volume.
+// Divisions are restated as products with reciprocals (one per distinct denominator); on the
+// device the fp32 reciprocals and the square root are single MUFU approximations (1-2 ulp), the
+// fp64 ones stay IEEE divisions — see the tolerances in tests/test_gpu_parity.py.
+template <class T, int D, bool SAME_RHO>
+SPH_HD void pair_fast(const Phys<T> &p, const FastTarget<T> &a, const T *xab, T r2, const T *va, const T *vb, T rho_b,
+                      T P_b, T rhon_b, bool fluid_b, bool a_is_i, T &drho, T *acc) {
+    // ∇W = fac * x_ab with fac = αD 5 (q−2)³ / (8h²), src/SPHKernels.jl:80-87.  q = clamp(d/h, 0, 2):
+    // the lower clamp is vacuous (d >= 0) and the upper one only guards the rounding of an accepted
+    // pair (r² <= H²); it is kept in fp64 and dropped in fp32 where (q−2)³ <= 1e-20 there.
+    T d = sph_sqrt_fast(r2);
+    T qm2 = (sizeof(T) == 8) ? sph_min(d * p.h_inv, T(2)) - T(2) : d * p.h_inv - T(2);
+    T fac = (p.gradw_c * qm2) * (qm2 * qm2);
     T vdotx = T(0);
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-        vab[k] = va[k] - vb[k];
-        vdotx += vab[k] * xab[k];
-    }
-    T vdotg = fac * vdotx;                          // v_ab · ∇W
+    for (int k = 0; k < D; ++k) vdotx += (va[k] - vb[k]) * xab[k];
+    T inv_rho_b = sph_rcp(rho_b);
+    T inv_rhon_b = SAME_RHO ? inv_rho_b : sph_rcp(rhon_b);
     // continuity, src/SPHCellList.jl:288-291: dρ/dt|a += ρ_a (m0/ρ_b) v_ab·∇W
-    T cont = rho_a * (p.m0 / rho_b) * vdotg;
-    // Linear density diffusion, src/SPHDensityDiffusionModels.jl:113-135
-    T inv = T(1) / (r2 + p.eta2);
-    T rho_H = p.ddt_lin * xab[D - 1];
-    T psi_dot_g = T(2) * ((rhon_b - rhon_a) - rho_H) * (-(fac * r2)) * inv;   // ψ·∇W
-    T vol = p.m0 / (a_is_i ? rhon_b : rhon_a);      // Q1: m0/ρ of the role-"j" particle
-    T Dd = p.ddt_k * vol * psi_dot_g * mlab;
-    drho += cont + Dd;
-    // momentum: pressure + artificial viscosity, :299-309, src/SPHViscosityModels.jl:56-74
-    T coef = -p.m0 * ((P_a + P_b) / (rho_a * rho_b));
-    if (vdotx < T(0)) {
-        T rho_bar = T(0.5) * (rhon_a + rhon_b);
-        T mu = p.h * vdotx * inv;
-        coef += p.m0 * (p.alpha * p.c0 * mu) / rho_bar;
-    }
+    drho += (a.c_cont * inv_rho_b) * (fac * vdotx);
+    // Linear density diffusion, src/SPHDensityDiffusionModels.jl:113-135:
+    //   D = δφ h c0 (m0/ρ_role-j) 2(ρ_b − ρ_a − ρᴴ)(−x_ab·∇W)/(r²+η²) ML_a ML_b     (Q1, Q2)
+    T inv = sph_rcp(r2 + p.eta2);
+    T diff = (rhon_b - a.rhon) - p.ddt_lin * xab[D - 1];
+    T dd = (a.c_ddt * (a_is_i ? inv_rhon_b : a.inv_rhon)) * (diff * ((fac * r2) * inv));
+    drho += fluid_b ? dd : T(0);
+    // momentum: pressure + artificial viscosity (only approaching pairs: min(v·x, 0)), :299-309,
+    // src/SPHViscosityModels.jl:56-74
+    T coef = (a.P + P_b) * (a.c_pres * inv_rho_b);
+    coef += (p.visc_k2 * (sph_min(vdotx, T(0)) * inv)) * sph_rcp(a.rhon + rhon_b);
     T cf = coef * fac;
 #pragma unroll
     for (int k = 0; k < D; ++k) acc[k] += cf * xab[k];
@@ -370,6 +413,7 @@ inline Phys<T> phys_from_params(const P &p) {
     ph.ddt_k = (T)(p.delta_phi * p.h * p.c0);
     ph.ddt_lin = (T)(p.rho0 * p.g * ((1.0 / (p.cb * p.gamma)) * p.rho0));
     ph.eos_b = (T)((p.c0 * p.c0 * p.rho0) / 7.0);
+    ph.visc_k2 = (T)(2.0 * p.m0 * p.alpha * p.c0 * p.h);
     ph.kernel = p.kernel; ph.viscosity = p.viscosity; ph.diffusion = p.diffusion;
     ph.shifting = p.shifting; ph.kernel_output = p.kernel_output; ph.mdbc = p.mdbc;
     ph.w_dx = T(1);

@@ -191,9 +191,12 @@ class Sim final : public sphb200_sim {
     SlabComm slab;
 
     Sim(const sphb200_params &p, int dev) : prm(p), device(dev) {
-        opt_compact = env_int("SPHB200_COMPACT", 1);
+        // defaults from the r1 sweeps on B200 (profiles/): the kernel is issue-bound and wants
+        // >= 6 CTAs/SM, i.e. a small staged window; with the MUFU-based fp32 pair body the
+        // divergent single-phase walk beats the two-phase lists, in fp64 the lists win
+        opt_compact = env_int("SPHB200_COMPACT", sizeof(T) == 8 ? 1 : 0);
         opt_tma = env_int("SPHB200_TMA", 1);
-        opt_smem_kb = env_int("SPHB200_SMEM_KB", 96);
+        opt_smem_kb = env_int("SPHB200_SMEM_KB", sizeof(T) == 8 ? 40 : 24);
         opt_batch = env_int("SPHB200_BATCH", 64);
         am.ax_s = D - 1;   // default: the reference's most significant axis
         am.ax_m = (D == 3) ? 1 : 0;

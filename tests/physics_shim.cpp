@@ -29,7 +29,10 @@ static void run(const sphb200_params *prm, int n, const double *pos, const doubl
             if (!(r2 <= ph.H2)) continue;
             bool role = a_is_i[(size_t)a * n + b] != 0;
             if (generic) pair_generic<T, D>(ph, A, B, xab, r2, role, s);
-            else pair_fast<T, D>(ph, xab, r2, A.v, B.v, A.rho, B.rho, A.P, B.P, A.rho_n, B.rho_n, A.ml * B.ml, role, fd, fa);
+            else {
+                FastTarget<T> ft = make_fast_target<T>(ph, A.rho, A.P, A.rho_n, A.ml, false);
+                pair_fast<T, D, false>(ph, ft, xab, r2, A.v, B.v, B.rho, B.P, B.rho_n, B.ml > T(0), role, fd, fa);
+            }
         }
         drho[a] = generic ? (double)s.drho : (double)fd;
         for (int k = 0; k < D; ++k) acc[a * D + k] = generic ? (double)s.acc[k] : (double)fa[k];
