@@ -23,6 +23,17 @@ struct AxisMap {
     int ax_m, ax_s;   // which position component is the m / s axis (x is always component 0)
 };
 
+// Which table entries take part in a rebuild (slab mode, sph_slab_impl.cuh).  Disabled: all of
+// [0, n).  Enabled: only [p0, p1) and [q0, n) are live, and a live particle whose slab coordinate
+// lies outside [keep_lo, keep_hi) is dropped (it has been handed to a neighbour rank).  Dropped
+// entries sort into a trash bucket behind the last cell and fall off the table.
+struct SlabFilter {
+    int enabled;
+    int p0, p1, q0;
+    int keep_lo, keep_hi;
+};
+constexpr int DEAD_COORD = INT_MIN;
+
 // map_floor, src/SPHCellList.jl:56-61: sign(x) * trunc(muladd(|x|, H⁻¹, 0.5)), evaluated in
 // double for both storage precisions so that an fp32 run bins exactly like the fp64 oracle fed
 // the same (fp32-representable) positions.
@@ -38,7 +49,7 @@ __device__ __forceinline__ int map_floor_dev(double x, double inv_cutoff, int &b
 
 template <class T, int D>
 __global__ void k_cell_bbox(const typename Lay<T, D>::TA *__restrict__ A, int n, double inv_cutoff,
-                            int *__restrict__ ccoord, Ctl *ctl, GridInfo *grid) {
+                            int *__restrict__ ccoord, Ctl *ctl, GridInfo *grid, AxisMap am, SlabFilter flt) {
     if (ctl->error || ctl->done || !ctl->do_rebuild) return;
     int lo[D], hi[D];
 #pragma unroll
@@ -48,14 +59,24 @@ __global__ void k_cell_bbox(const typename Lay<T, D>::TA *__restrict__ A, int n,
     }
     int bad = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        T x[D];
-        Lay<T, D>::pos(A[i], x);
+        bool live = !flt.enabled || (i >= flt.p0 && i < flt.p1) || i >= flt.q0;
+        int c[D];
+        if (live) {
+            T x[D];
+            Lay<T, D>::pos(A[i], x);
+#pragma unroll
+            for (int k = 0; k < D; ++k) c[k] = map_floor_dev((double)x[k], inv_cutoff, bad);
+            if (flt.enabled && (c[am.ax_s] < flt.keep_lo || c[am.ax_s] >= flt.keep_hi)) live = false;
+        }
+        if (!live) {
+            ccoord[(size_t)i * D] = DEAD_COORD;
+            continue;
+        }
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            int c = map_floor_dev((double)x[k], inv_cutoff, bad);
-            ccoord[(size_t)i * D + k] = c;
-            lo[k] = min(lo[k], c);
-            hi[k] = max(hi[k], c);
+            ccoord[(size_t)i * D + k] = c[k];
+            lo[k] = min(lo[k], c[k]);
+            hi[k] = max(hi[k], c[k]);
         }
     }
 #pragma unroll
@@ -129,7 +150,13 @@ __global__ void k_cell_count(const int *__restrict__ ccoord, int n, AxisMap am, 
     if (ctl->error || ctl->done || !ctl->do_rebuild) return;
     const int nx = grid->nx, nm = grid->nm;
     const int cx0 = grid->cmin[0], cm0 = (D == 3) ? grid->cmin[am.ax_m] : 0, cs0 = grid->cmin[am.ax_s];
+    const int trash = grid->ncell;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (ccoord[(size_t)i * D] == DEAD_COORD) {
+            key_out[i] = trash;
+            slot_out[i] = atomicAdd(&cell_count[trash], 1);
+            continue;
+        }
         int cx = ccoord[(size_t)i * D + 0] - cx0;
         int cm = (D == 3) ? ccoord[(size_t)i * D + am.ax_m] - cm0 : 0;
         int cs = ccoord[(size_t)i * D + am.ax_s] - cs0;
@@ -240,16 +267,40 @@ __global__ void k_scatter_unstable(const Ctl *ctl, const int *__restrict__ key, 
         tmp_idx[cell_start[key[i]] + slot[i]] = i;
 }
 
-// stable order inside each cell = ascending previous index
-__global__ void k_stable_rank(const Ctl *ctl, const int *__restrict__ key, const int *__restrict__ tmp_idx, int n,
-                              const int *__restrict__ cell_start, int *__restrict__ perm) {
+// Stable order inside each cell.  The reference's stable sort keeps, inside a cell, the order of
+// the table before the sort, and that table was ordered by (previous cell in the reference's
+// column-major cell order, order inside that cell).  The per-particle ORDER KEY carries exactly
+// this pair — (reference cell key of the previous rebuild) << 10 | (rank inside that cell) — so
+// the within-cell order (which decides the density-diffusion roles of same-cell pairs)
+// is reproduced even when this table is sorted with another major axis or split over ranks.
+// On one GPU with the default axes it coincides with "ascending previous index".
+constexpr int OKEY_RANK_BITS = 10;
+constexpr int OKEY_AXIS_BITS = 18;
+template <int D>
+__device__ __forceinline__ unsigned long long order_key(const int *c, int rank) {
+    unsigned long long k = 0;
+    const int off = 1 << (OKEY_AXIS_BITS - 1), lim = (1 << OKEY_AXIS_BITS) - 1;
+#pragma unroll
+    for (int a = D - 1; a >= 0; --a) k = (k << OKEY_AXIS_BITS) | (unsigned long long)min(max(c[a] + off, 0), lim);
+    return (k << OKEY_RANK_BITS) | (unsigned long long)min(rank, (1 << OKEY_RANK_BITS) - 1);
+}
+
+__global__ void k_stable_rank(const Ctl *ctl, const GridInfo *grid, const int *__restrict__ key,
+                              const int *__restrict__ tmp_idx, int n, const int *__restrict__ cell_start,
+                              const unsigned long long *__restrict__ okey, int *__restrict__ perm) {
     if (ctl->error || ctl->done || !ctl->do_rebuild) return;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    const int nlive = cell_start[grid->ncell];   // entries behind it are the trash bucket
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nlive; p += gridDim.x * blockDim.x) {
         int v = tmp_idx[p];
         int c = key[v];
         int s = cell_start[c], e = cell_start[c + 1];
+        const unsigned long long kv = okey[v];
         int rank = 0;
-        for (int q = s; q < e; ++q) rank += (tmp_idx[q] < v);
+        for (int q = s; q < e; ++q) {
+            int u = tmp_idx[q];
+            unsigned long long ku = okey[u];
+            rank += (ku < kv) | ((ku == kv) & (u < v));
+        }
         perm[s + rank] = v;
     }
 }
@@ -263,14 +314,17 @@ struct Table {
     typename Lay<T, D>::TV *ghost;   // may be null
     long long *id;
     unsigned long long *group;
+    unsigned long long *okey;        // within-cell order key, see k_stable_rank
     uint8_t *type;
     int *ckey;
 };
 
 template <class T, int D>
-__global__ void k_gather_table(const Ctl *ctl, const int *__restrict__ perm, int n, Table<T, D> src, Table<T, D> dst,
-                               const int *__restrict__ key_prev_order) {
+__global__ void k_gather_table(const Ctl *ctl, const GridInfo *grid, const int *__restrict__ cell_start,
+                               const int *__restrict__ perm, Table<T, D> src, Table<T, D> dst,
+                               const int *__restrict__ key_prev_order, const int *__restrict__ ccoord_prev_order) {
     if (ctl->error || ctl->done || !ctl->do_rebuild) return;
+    const int n = cell_start[grid->ncell];
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         int s = perm[p];
         dst.A[p] = src.A[s];
@@ -280,13 +334,20 @@ __global__ void k_gather_table(const Ctl *ctl, const int *__restrict__ perm, int
         dst.id[p] = src.id[s];
         dst.group[p] = src.group[s];
         dst.type[p] = src.type[s];
-        dst.ckey[p] = key_prev_order[s];
+        const int key = key_prev_order[s];
+        dst.ckey[p] = key;
+        int c[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) c[k] = ccoord_prev_order[(size_t)s * D + k];
+        dst.okey[p] = order_key<D>(c, p - cell_start[key]);
     }
 }
 
 template <class T, int D>
-__global__ void k_copy_table(const Ctl *ctl, int n, Table<T, D> src, Table<T, D> dst) {
+__global__ void k_copy_table(const Ctl *ctl, const GridInfo *grid, const int *__restrict__ cell_start,
+                             Table<T, D> src, Table<T, D> dst) {
     if (ctl->error || ctl->done || !ctl->do_rebuild) return;
+    const int n = cell_start[grid->ncell];
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         dst.A[p] = src.A[p];
         dst.B[p] = src.B[p];
@@ -295,6 +356,7 @@ __global__ void k_copy_table(const Ctl *ctl, int n, Table<T, D> src, Table<T, D>
         dst.id[p] = src.id[p];
         dst.group[p] = src.group[p];
         dst.type[p] = src.type[p];
+        dst.okey[p] = src.okey[p];
         dst.ckey[p] = src.ckey[p];
     }
 }
@@ -302,7 +364,7 @@ __global__ void k_copy_table(const Ctl *ctl, int n, Table<T, D> src, Table<T, D>
 // Brick list: every owned row (c_m, c_s) of cells is cut into segments of at most `bt`
 // consecutive particles; one brick is the unit of work of the interaction kernel.
 __global__ void k_build_bricks(Ctl *ctl, GridInfo *grid, const int *__restrict__ cell_start, int bt,
-                               Brick *__restrict__ bricks, int brick_cap, int n) {
+                               Brick *__restrict__ bricks, int brick_cap, int count_rebuild) {
     if (ctl->error || ctl->done || !ctl->do_rebuild) return;
     __shared__ int sw[33];
     __shared__ int s_carry;
@@ -341,8 +403,11 @@ __global__ void k_build_bricks(Ctl *ctl, GridInfo *grid, const int *__restrict__
         }
         grid->own_p0 = cell_start[(size_t)r0 * nx];
         grid->own_p1 = cell_start[(size_t)r1 * nx];
-        grid->n_total = n;
-        ctl->n_rebuilds += 1;
+        const int nm = grid->nm;
+        grid->own_l1 = cell_start[(size_t)min(r0 + nm, r1) * nx];
+        grid->own_l2 = cell_start[(size_t)max(r1 - nm, r0) * nx];
+        grid->n_total = cell_start[grid->ncell];
+        ctl->n_rebuilds += count_rebuild;
     }
 }
 

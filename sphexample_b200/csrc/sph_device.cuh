@@ -87,6 +87,7 @@ struct Ctl {
     int pad0;
     // reductions feeding Δt and Δx (bit patterns of non-negative reals, atomicMax-ed)
     unsigned long long red_disp2, red_visc, red_acc2;
+    unsigned long long red_err;   // slab mode: max over ranks of -error (all-reduced with the three above)
     // work distribution of the interaction kernel
     int work_counter[2];
 };
@@ -98,6 +99,7 @@ struct GridInfo {
     int ncell, nrows, nbricks;
     int own_row0, own_row1;    // rows [own_row0, own_row1) are owned by this rank (slab mode)
     int own_p0, own_p1;        // owned particle index range in sorted order
+    int own_l1, own_l2;        // [own_p0, own_l1) = first owned slab layer, [own_l2, own_p1) = last one
     int n_total;               // particles on this rank (owned + halo)
 };
 

@@ -1,20 +1,325 @@
 // sph_slab_impl.cuh — slab-mode member functions of Sim<T, D> (included by sphb200.cu).
+// See sph_slab.cuh for the decomposition and the exchange protocol.
 #pragma once
 
 namespace sph {
+
 int slab_unique_id(uint8_t *id_out) {
-    (void)id_out;
-    return SPHB200_ENCCL;
+    std::string err;
+    if (!id_out || !nccl::api().load(err)) return SPHB200_ENCCL;
+    nccl::UniqueId id;
+    memset(&id, 0, sizeof id);
+    if (nccl::api().GetUniqueId(&id) != nccl::Success) return SPHB200_ENCCL;
+    memcpy(id_out, &id, 128);
+    return SPHB200_OK;
 }
+
+// gather `cnt` table records listed in `list` into dst[off .. off+cnt)
+template <class T, int D>
+__global__ void k_slab_pack(const int *__restrict__ list, int cnt, int off, Table<T, D> src, Table<T, D> dst) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += gridDim.x * blockDim.x) {
+        int s = list[k], p = off + k;
+        dst.A[p] = src.A[s];
+        dst.B[p] = src.B[s];
+        dst.acc[p] = src.acc[s];
+        dst.id[p] = src.id[s];
+        dst.group[p] = src.group[s];
+        dst.okey[p] = src.okey[s];
+        dst.type[p] = src.type[s];
+    }
+}
+
 }  // namespace sph
 
 namespace {
+
+#define CKS(call)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(SPHB200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define NCK(call)                                                                                         \
+    do {                                                                                                  \
+        int r_ = (call);                                                                                  \
+        if (r_ != nccl::Success)                                                                          \
+            return fail(SPHB200_ENCCL, "%s failed: %s (%s:%d)", #call, nccl::api().GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
 template <class T, int D>
-int Sim<T, D>::comm_init(const uint8_t *, int, int, int) { return fail(SPHB200_ENCCL, "slab mode not available in this build"); }
+int Sim<T, D>::comm_init(const uint8_t *uid, int rank, int world, int axis) {
+    if (!uid || world < 1 || rank < 0 || rank >= world) return fail(SPHB200_EINVAL, "comm_init: bad rank/world");
+    if (axis < 1 || axis >= D)
+        return fail(SPHB200_EINVAL, "comm_init: the slab axis must be 1..%d (x is the fastest key component: a cell row "
+                                    "must stay on one rank)", D - 1);
+    if (prm.mdbc) return fail(SPHB200_EINVAL, "comm_init: SimpleMDBC is single-GPU only (ghost nodes reach two cells across a slab face)");
+    if (slab.active) return fail(SPHB200_ESTATE, "comm_init: communicator already initialised");
+    if (uploaded) return fail(SPHB200_ESTATE, "comm_init must precede upload");
+    CKS(cudaSetDevice(device));
+    std::string e;
+    if (!nccl::api().load(e)) return fail(SPHB200_ENCCL, "%s", e.c_str());
+    nccl::UniqueId id;
+    memcpy(&id, uid, 128);
+    NCK(nccl::api().CommInitRank(&slab.comm, world, id, rank));
+    slab.rank = rank;
+    slab.world = world;
+    slab.left = rank > 0 ? rank - 1 : -1;
+    slab.right = rank + 1 < world ? rank + 1 : -1;
+    CKS(cudaMalloc((void **)&slab.d_counts, 8 * sizeof(int)));
+    CKS(cudaMallocHost((void **)&slab.h_counts, 8 * sizeof(int)));
+    am.ax_s = axis;
+    am.ax_m = (D == 3) ? (axis == 1 ? 2 : 1) : 0;
+    ref_major_is_s = (D == 2) || (am.ax_s > am.ax_m);
+    slab.active = true;
+    return SPHB200_OK;
+}
+
 template <class T, int D>
-int Sim<T, D>::set_slab(int64_t, int64_t) { return fail(SPHB200_ENCCL, "slab mode not available in this build"); }
+int Sim<T, D>::set_slab(int64_t lo, int64_t hi) {
+    if (!slab.active) return fail(SPHB200_ESTATE, "set_slab before comm_init");
+    if (hi - lo < 2 && lo != INT64_MIN && hi != INT64_MAX) return fail(SPHB200_EINVAL, "a slab must be at least 2 cell layers wide");
+    own_lo = lo <= (int64_t)INT_MIN ? INT_MIN : (int)lo;
+    own_hi = hi >= (int64_t)INT_MAX ? INT_MAX : (int)hi;
+    if (slab.left < 0) own_lo = INT_MIN;
+    if (slab.right < 0) own_hi = INT_MAX;
+    return SPHB200_OK;
+}
+
 template <class T, int D>
-int Sim<T, D>::column_histogram(int, int64_t *, int64_t *, int64_t *, int64_t) { return fail(SPHB200_ENCCL, "slab mode not available in this build"); }
+int Sim<T, D>::column_histogram(int axis, int64_t *cell_min, int64_t *n_columns, int64_t *counts, int64_t cap) {
+    if (!uploaded) return fail(SPHB200_ESTATE, "column_histogram before upload");
+    if (axis < 0 || axis >= D || !cell_min || !n_columns) return fail(SPHB200_EINVAL, "column_histogram: bad arguments");
+    CKS(cudaSetDevice(device));
+    // range of cell coordinates along `axis`: from a fresh bounding box of the owned particles
+    const int p0 = slab.active ? slab.own_p0 : 0, p1 = slab.active ? slab.own_p1 : (int)n;
+    std::vector<T> hx((size_t)(p1 - p0) * (sizeof(TA) / sizeof(T)));
+    CKS(cudaMemcpyAsync(hx.data(), A.p + p0, (size_t)(p1 - p0) * sizeof(TA), cudaMemcpyDeviceToHost, stream));
+    CKS(cudaStreamSynchronize(stream));
+    const int stride = sizeof(TA) / sizeof(T);
+    auto cell = [&](double x) { double t = trunc(fma(fabs(x), prm.H_inv, 0.5)); return (int64_t)(((x > 0) - (x < 0)) * t); };
+    int64_t cmin = INT64_MAX, cmax = INT64_MIN;
+    for (int i = 0; i < p1 - p0; ++i) {
+        int64_t c = cell((double)hx[(size_t)i * stride + axis]);
+        cmin = std::min(cmin, c);
+        cmax = std::max(cmax, c);
+    }
+    if (p1 <= p0) { cmin = 0; cmax = -1; }
+    *cell_min = cmin;
+    *n_columns = cmax - cmin + 1;
+    if (counts) {
+        if (cap < *n_columns) return fail(SPHB200_ECAPACITY, "column_histogram: need room for %lld columns", (long long)*n_columns);
+        for (int64_t k = 0; k < *n_columns; ++k) counts[k] = 0;
+        for (int i = 0; i < p1 - p0; ++i) counts[cell((double)hx[(size_t)i * stride + axis]) - cmin] += 1;
+    }
+    return SPHB200_OK;
+}
+
+// ---- small exchanges --------------------------------------------------------------------------
+// d_counts[0], [1] -> left, right neighbour; their values arrive in d_counts[2] (from left), [3] (from right)
 template <class T, int D>
-int Sim<T, D>::run_steps_slab(int64_t, bool) { return fail(SPHB200_ENCCL, "slab mode not available in this build"); }
+int Sim<T, D>::slab_exchange_counts(int to_left, int to_right, int *from_left, int *from_right) {
+    slab.h_counts[0] = to_left;
+    slab.h_counts[1] = to_right;
+    slab.h_counts[2] = slab.h_counts[3] = 0;
+    CKS(cudaMemcpyAsync(slab.d_counts, slab.h_counts, 4 * sizeof(int), cudaMemcpyHostToDevice, stream));
+    NCK(nccl::api().GroupStart());
+    if (slab.left >= 0) {
+        NCK(nccl::api().Send(slab.d_counts + 0, 1, nccl::Int32, slab.left, slab.comm, stream));
+        NCK(nccl::api().Recv(slab.d_counts + 2, 1, nccl::Int32, slab.left, slab.comm, stream));
+    }
+    if (slab.right >= 0) {
+        NCK(nccl::api().Send(slab.d_counts + 1, 1, nccl::Int32, slab.right, slab.comm, stream));
+        NCK(nccl::api().Recv(slab.d_counts + 3, 1, nccl::Int32, slab.right, slab.comm, stream));
+    }
+    NCK(nccl::api().GroupEnd());
+    CKS(cudaMemcpyAsync(slab.h_counts, slab.d_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CKS(cudaStreamSynchronize(stream));
+    *from_left = slab.h_counts[2];
+    *from_right = slab.h_counts[3];
+    return SPHB200_OK;
+}
+
+// full records: src ranges [sl0, sl0+nl) -> left, [sr0, sr0+nr) -> right of table `from`;
+// arrivals are appended to table(false) at dst0 (left's block first)
+template <class T, int D>
+int Sim<T, D>::slab_exchange_records(Table<T, D> from, int sl0, int nl, int sr0, int nr, int dst0, int rl, int rr) {
+    Table<T, D> to = table(false);
+    NCK(nccl::api().GroupStart());
+    auto xfer = [&](auto *src, auto *dst) -> int {
+        const size_t es = sizeof(*src);
+        if (slab.left >= 0) {
+            if (nl) NCK(nccl::api().Send(src + sl0, (size_t)nl * es, nccl::Int8, slab.left, slab.comm, stream));
+            if (rl) NCK(nccl::api().Recv(dst + dst0, (size_t)rl * es, nccl::Int8, slab.left, slab.comm, stream));
+        }
+        if (slab.right >= 0) {
+            if (nr) NCK(nccl::api().Send(src + sr0, (size_t)nr * es, nccl::Int8, slab.right, slab.comm, stream));
+            if (rr) NCK(nccl::api().Recv(dst + dst0 + rl, (size_t)rr * es, nccl::Int8, slab.right, slab.comm, stream));
+        }
+        return 0;
+    };
+    int rc;
+    if ((rc = xfer(from.A, to.A))) return rc;
+    if ((rc = xfer(from.B, to.B))) return rc;
+    if ((rc = xfer(from.acc, to.acc))) return rc;
+    if ((rc = xfer(from.id, to.id))) return rc;
+    if ((rc = xfer(from.group, to.group))) return rc;
+    if ((rc = xfer(from.okey, to.okey))) return rc;
+    if ((rc = xfer(from.type, to.type))) return rc;
+    NCK(nccl::api().GroupEnd());
+    return SPHB200_OK;
+}
+
+// the half-step exchange: boundary layers of two packed arrays to the neighbours' halo ranges
+template <class T, int D>
+int Sim<T, D>::slab_exchange_halo(TA *a, TB *b) {
+    const SlabComm &s = slab;
+    const int nf = s.l1 - s.own_p0, nl = s.own_p1 - s.l2, hl = s.own_p0, hr = (int)n - s.own_p1;
+    NCK(nccl::api().GroupStart());
+    if (s.left >= 0) {
+        if (nf) {
+            NCK(nccl::api().Send(a + s.own_p0, (size_t)nf * sizeof(TA), nccl::Int8, s.left, s.comm, stream));
+            NCK(nccl::api().Send(b + s.own_p0, (size_t)nf * sizeof(TB), nccl::Int8, s.left, s.comm, stream));
+        }
+        if (hl) {
+            NCK(nccl::api().Recv(a, (size_t)hl * sizeof(TA), nccl::Int8, s.left, s.comm, stream));
+            NCK(nccl::api().Recv(b, (size_t)hl * sizeof(TB), nccl::Int8, s.left, s.comm, stream));
+        }
+    }
+    if (s.right >= 0) {
+        if (nl) {
+            NCK(nccl::api().Send(a + s.l2, (size_t)nl * sizeof(TA), nccl::Int8, s.right, s.comm, stream));
+            NCK(nccl::api().Send(b + s.l2, (size_t)nl * sizeof(TB), nccl::Int8, s.right, s.comm, stream));
+        }
+        if (hr) {
+            NCK(nccl::api().Recv(a + s.own_p1, (size_t)hr * sizeof(TA), nccl::Int8, s.right, s.comm, stream));
+            NCK(nccl::api().Recv(b + s.own_p1, (size_t)hr * sizeof(TB), nccl::Int8, s.right, s.comm, stream));
+        }
+    }
+    NCK(nccl::api().GroupEnd());
+    return SPHB200_OK;
+}
+
+template <class T, int D>
+int Sim<T, D>::slab_allreduce_ctl() {
+    k_slab_pre_allreduce<<<1, 1, 0, stream>>>(d_ctl.p);
+    ++launches;
+    NCK(nccl::api().AllReduce(&d_ctl.p->red_disp2, &d_ctl.p->red_disp2, 4, nccl::Uint64, nccl::Max, slab.comm, stream));
+    return SPHB200_OK;
+}
+
+// one sort of the live part of the table (retrying after a dense-grid growth)
+template <class T, int D>
+int Sim<T, D>::slab_sort(const SlabFilter &flt, int count_rebuild) {
+    int rc;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        if ((rc = force_flag_rebuild())) return rc;
+        if ((rc = enqueue_rebuild(flt, count_rebuild))) return rc;
+        if ((rc = sync_ctl())) return rc;
+        if (h_ctl->error != SPHB200_ECAPACITY) break;
+        if ((rc = recover_capacity())) return rc;
+    }
+    if (h_ctl->error) return fail(h_ctl->error, "slab rebuild: device reported error %d", h_ctl->error);
+    return SPHB200_OK;
+}
+
+// UpdateNeighbors! across slabs: migrate, sort the owned set, swap boundary layers, sort again
+template <class T, int D>
+int Sim<T, D>::slab_rebuild() {
+    int rc;
+    SlabComm &s = slab;
+    const int n_old = (int)n;
+    // 1. owned particles that left the slab
+    CKS(cudaMemsetAsync(s.d_counts + 4, 0, 2 * sizeof(int), stream));
+    k_slab_classify<T, D><<<grid_for(s.own_p1 - s.own_p0), 256, 0, stream>>>(A.p, s.own_p0, s.own_p1, prm.H_inv, am.ax_s, own_lo,
+                                                                            own_hi, tmp_idx.p, perm.p, s.d_counts + 4, d_ctl.p);
+    ++launches;
+    CKS(cudaMemcpyAsync(s.h_counts + 4, s.d_counts + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CKS(cudaStreamSynchronize(stream));
+    const int ml = s.h_counts[4], mr = s.h_counts[5];
+    // deterministic order of the migrants: ascending table index (the atomics append in any order)
+    auto sort_list = [&](int *dlist, int cnt) -> int {
+        if (cnt < 2) return 0;
+        std::vector<int> h((size_t)cnt);
+        CKS(cudaMemcpyAsync(h.data(), dlist, (size_t)cnt * 4, cudaMemcpyDeviceToHost, stream));
+        CKS(cudaStreamSynchronize(stream));
+        std::sort(h.begin(), h.end());
+        CKS(cudaMemcpyAsync(dlist, h.data(), (size_t)cnt * 4, cudaMemcpyHostToDevice, stream));
+        CKS(cudaStreamSynchronize(stream));
+        return 0;
+    };
+    if ((rc = sort_list(tmp_idx.p, ml))) return rc;
+    if ((rc = sort_list(perm.p, mr))) return rc;
+    if (ml) k_slab_pack<T, D><<<grid_for(ml), 256, 0, stream>>>(tmp_idx.p, ml, 0, table(false), table(true));
+    if (mr) k_slab_pack<T, D><<<grid_for(mr), 256, 0, stream>>>(perm.p, mr, ml, table(false), table(true));
+    launches += (ml > 0) + (mr > 0);
+    int rl = 0, rr = 0;
+    if ((rc = slab_exchange_counts(ml, mr, &rl, &rr))) return rc;
+    if ((rc = grow_particles((int64_t)n_old + rl + rr))) return rc;
+    if ((rc = slab_exchange_records(table(true), 0, ml, ml, mr, n_old, rl, rr))) return rc;
+    if (rl + rr) {
+        k_slab_check_arrivals<T, D><<<grid_for(rl + rr), 256, 0, stream>>>(A.p, n_old, n_old + rl + rr, prm.H_inv, am.ax_s, own_lo,
+                                                                           own_hi, d_ctl.p);
+        ++launches;
+    }
+    s.n_migrated += ml + mr;
+    // 2. sort A: the owned set only (old halo copies and the migrants that left are dropped)
+    n = n_old + rl + rr;
+    SlabFilter fa = {1, s.own_p0, s.own_p1, n_old, own_lo, own_hi};
+    if ((rc = slab_sort(fa, 0))) return rc;
+    n = h_grid->n_total;
+    if (n < 1) return fail(SPHB200_ESTATE, "rank %d owns no particles (slab [%d, %d))", s.rank, own_lo, own_hi);
+    const int cf = h_grid->own_l1 - h_grid->own_p0, cl = h_grid->own_p1 - h_grid->own_l2;
+    const int l2 = h_grid->own_l2;
+    // 3. boundary layers -> neighbours' halos (full records), then sort B over owned + halo
+    int hl = 0, hr = 0;
+    if ((rc = slab_exchange_counts(cf, cl, &hl, &hr))) return rc;
+    if ((rc = grow_particles(n + hl + hr))) return rc;
+    if ((rc = slab_exchange_records(table(false), 0, cf, l2, cl, (int)n, hl, hr))) return rc;
+    n += hl + hr;
+    SlabFilter fb = {0, 0, 0, 0, 0, 0};
+    if ((rc = slab_sort(fb, 1))) return rc;
+    s.own_p0 = h_grid->own_p0;
+    s.own_p1 = h_grid->own_p1;
+    s.l1 = h_grid->own_l1;
+    s.l2 = h_grid->own_l2;
+    if (s.own_p0 != hl || (int)n - s.own_p1 != hr || h_grid->n_total != (int)n)
+        return fail(SPHB200_ESTATE, "slab rebuild: halo layers are not where expected (left %d/%d, right %d/%d)", s.own_p0, hl,
+                    (int)n - s.own_p1, hr);
+    s.halo_bytes_per_step = 2ll * ((s.l1 - s.own_p0) * (s.left >= 0) + (s.own_p1 - s.l2) * (s.right >= 0)) * (long long)(sizeof(TA) + sizeof(TB));
+    return SPHB200_OK;
+}
+
+template <class T, int D>
+int Sim<T, D>::run_steps_slab(int64_t nsteps, bool until_target) {
+    int rc = sync_ctl();
+    if (rc) return rc;
+    int64_t done_steps = 0;
+    while (until_target || done_steps < nsteps) {
+        if ((rc = enqueue_step_head())) return rc;
+        if ((rc = sync_ctl())) return rc;
+        if (h_ctl->error == SPHB200_ENUMERIC)
+            return fail(SPHB200_ENUMERIC, "non-finite state or time step at iteration %lld (t = %g)", h_ctl->iteration, h_ctl->total_time);
+        if (h_ctl->error) return fail(h_ctl->error, "device reported error %d (rank %d)", h_ctl->error, slab.rank);
+        if (until_target && h_ctl->done) break;
+        if (h_ctl->do_rebuild && (rc = slab_rebuild())) return rc;
+        if ((rc = enqueue_motion(-1.0))) return rc;                       // S3
+        if ((rc = enqueue_snapshots())) return rc;
+        if ((rc = launch_interact(0, EPI_FUSED))) return rc;              // S4-S10, S13 (owned bricks)
+        if ((rc = enqueue_motion(-1.0))) return rc;                       // S12
+        if ((rc = slab_exchange_halo(Ah.p, Bh.p))) return rc;             // state n+½ of the halo layers
+        if ((rc = launch_interact(1, EPI_FUSED))) return rc;              // S11, S14-S18
+        k_step_end<<<1, 1, 0, stream>>>(d_ctl.p);                         // S19
+        ++launches;
+        if ((rc = slab_exchange_halo(A.p, B.p))) return rc;               // state n+1 of the halo layers
+        have_half = true;
+        have_cells = true;
+        ++done_steps;
+    }
+    if ((rc = sync_ctl())) return rc;
+    if (h_ctl->error) return fail(h_ctl->error, "device reported error %d (rank %d)", h_ctl->error, slab.rank);
+    return SPHB200_OK;
+}
+
+#undef CKS
+#undef NCK
 }  // namespace

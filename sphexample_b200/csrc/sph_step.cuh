@@ -69,6 +69,8 @@ __global__ void k_reduce_dt_dx(const typename Lay<T, D>::TA *__restrict__ A, con
 // (:742).  Arithmetic is carried out in T like the reference's (its scalars are ::T).
 template <class T>
 __global__ void k_step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl) {
+    if (ctl->red_err && !ctl->error) ctl->error = -(int)ctl->red_err;   // slab mode: another rank failed
+    ctl->red_err = 0ull;
     if (ctl->error) return;
     // consume the reductions unconditionally so that nothing stale survives a skipped step
     T disp = sph_sqrt((T)bits_to_double(ctl->red_disp2));

@@ -78,6 +78,21 @@ struct DevBuf {
         if (e == cudaSuccess) n = count;
         return e;
     }
+    // enlarge to `count` elements keeping the first `keep` (stream-ordered copy, then free)
+    cudaError_t grow(size_t count, size_t keep, cudaStream_t st) {
+        if (count <= n && p) return cudaSuccess;
+        T *q = nullptr;
+        cudaError_t e = cudaMalloc((void **)&q, std::max<size_t>(count, 1) * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (p && keep) {
+            e = cudaMemcpyAsync(q, p, std::min(keep, n) * sizeof(T), cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+        if (p) cudaFree(p);
+        p = q;
+        n = count;
+        return e;
+    }
     void release() {
         if (p) cudaFree(p);
         p = nullptr;
@@ -90,7 +105,8 @@ template <class T, int D>
 __global__ void k_pack_upload(int n, const T *__restrict__ pos, const T *__restrict__ vel, const T *__restrict__ acc,
                               const T *__restrict__ rho, const T *__restrict__ ghost, const uint8_t *__restrict__ type,
                               Phys<T> ph, typename Lay<T, D>::TA *A, typename Lay<T, D>::TB *B,
-                              typename Lay<T, D>::TV *accv, typename Lay<T, D>::TV *ghostv) {
+                              typename Lay<T, D>::TV *accv, typename Lay<T, D>::TV *ghostv,
+                              const long long *__restrict__ ids, unsigned long long *okey) {
     using L = Lay<T, D>;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         T x[D], v[D], a[D], gp[D];
@@ -109,6 +125,9 @@ __global__ void k_pack_upload(int n, const T *__restrict__ pos, const T *__restr
         B[i] = ob;
         accv[i] = L::mkv(a);
         if (ghostv) ghostv[i] = L::mkv(gp);
+        // initial within-cell order = table order (single GPU) / ascending ID (slab mode, where
+        // each rank holds a subset of the reference's ID-sorted table, src/PreProcess.jl:116)
+        okey[i] = ids ? (unsigned long long)ids[i] : (unsigned long long)i;
     }
 }
 
@@ -174,7 +193,7 @@ class Sim final : public sphb200_sim {
     DevBuf<TV> acc, acc2, ghost, ghost2, gradC, kgrad;
     DevBuf<T> RN, drhodt, divr, ksum, rho_new;
     DevBuf<long long> id, id2;
-    DevBuf<unsigned long long> group, group2;
+    DevBuf<unsigned long long> group, group2, okey, okey2;
     DevBuf<uint8_t> type, type2, has_new;
     DevBuf<int> ckey, ckey2, ccoord, key_tmp, slot_tmp, tmp_idx, perm;
     // cell structure
@@ -203,6 +222,9 @@ class Sim final : public sphb200_sim {
         build_phys();
     }
     ~Sim() override {
+        if (slab.comm) nccl::api().CommDestroy(slab.comm);
+        if (slab.d_counts) cudaFree(slab.d_counts);
+        if (slab.h_counts) cudaFreeHost(slab.h_counts);
         if (h_ctl) cudaFreeHost(h_ctl);
         if (h_grid) cudaFreeHost(h_grid);
         if (own_stream && stream) cudaStreamDestroy(stream);
@@ -295,6 +317,7 @@ class Sim final : public sphb200_sim {
         CK(acc.alloc(na)); CK(acc2.alloc(na));
         CK(RN.alloc(na)); CK(drhodt.alloc(na));
         CK(id.alloc(na)); CK(id2.alloc(na)); CK(group.alloc(na)); CK(group2.alloc(na));
+        CK(okey.alloc(na)); CK(okey2.alloc(na));
         CK(type.alloc(na)); CK(type2.alloc(na));
         CK(ckey.alloc(na)); CK(ckey2.alloc(na)); CK(ccoord.alloc(na * D));
         CK(key_tmp.alloc(na)); CK(slot_tmp.alloc(na)); CK(tmp_idx.alloc(na)); CK(perm.alloc(na));
@@ -309,6 +332,31 @@ class Sim final : public sphb200_sim {
         CK(cudaMemsetAsync(acc.p, 0, na * sizeof(TV), stream));
         n_alloc = na;
         return SPHB200_OK;
+    }
+    // slab mode: make room for `count` table entries, keeping what the table and the send scratch hold
+    int grow_particles(int64_t count) {
+        size_t na = (size_t)((count + 3) & ~3ll) + 8;
+        if (na <= n_alloc) return SPHB200_OK;
+        na = na + na / 4;
+        const size_t keep = n_alloc;
+        CK(A.grow(na, keep, stream)); CK(A2.grow(na, keep, stream)); CK(Ah.grow(na, keep, stream));
+        CK(B.grow(na, keep, stream)); CK(B2.grow(na, keep, stream)); CK(Bh.grow(na, keep, stream));
+        CK(acc.grow(na, keep, stream)); CK(acc2.grow(na, keep, stream));
+        CK(RN.grow(na, keep, stream)); CK(drhodt.grow(na, keep, stream));
+        CK(id.grow(na, keep, stream)); CK(id2.grow(na, keep, stream));
+        CK(group.grow(na, keep, stream)); CK(group2.grow(na, keep, stream));
+        CK(okey.grow(na, keep, stream)); CK(okey2.grow(na, keep, stream));
+        CK(type.grow(na, keep, stream)); CK(type2.grow(na, keep, stream));
+        CK(ckey.grow(na, keep, stream)); CK(ckey2.grow(na, 0, stream)); CK(ccoord.grow(na * D, 0, stream));
+        CK(key_tmp.grow(na, 0, stream)); CK(slot_tmp.grow(na, 0, stream)); CK(tmp_idx.grow(na, 0, stream)); CK(perm.grow(na, 0, stream));
+        if (prm.shifting) { CK(gradC.grow(na, keep, stream)); CK(divr.grow(na, keep, stream)); }
+        if (prm.kernel_output) { CK(ksum.grow(na, keep, stream)); CK(kgrad.grow(na, keep, stream)); }
+        CK(stage.grow(na * (size_t)(sizeof(T) * (4 * D + 2) + 8), 0, stream));
+        n_alloc = na;
+        brick_cap = 0;   // re-sized with the cell tables
+        long long cc = cell_cap;
+        cell_cap = 0;
+        return alloc_cells(cc);
     }
     int alloc_cells(long long cells_needed) {
         long long cap = std::max<long long>(cells_needed, 4096);
@@ -366,7 +414,8 @@ class Sim final : public sphb200_sim {
         k_pack_upload<T, D><<<grid_for(count), 256, 0, stream>>>((int)count, d_pos, vel ? d_vel : nullptr,
                                                                 accel ? d_acc : nullptr, d_rho,
                                                                 (gp && prm.mdbc) ? d_gp : nullptr, type.p, ph, A.p, B.p,
-                                                                acc.p, prm.mdbc ? ghost.p : nullptr);
+                                                                acc.p, prm.mdbc ? ghost.p : nullptr,
+                                                                slab.active ? id.p : nullptr, okey.p);
         ++launches;
         CK(cudaGetLastError());
         // size the dense cell grid from the host-side bounding box (grown on demand later)
@@ -396,6 +445,8 @@ class Sim final : public sphb200_sim {
         have_cells = false;
         have_half = false;
         uploaded = true;
+        slab.own_p0 = slab.l1 = 0;
+        slab.own_p1 = slab.l2 = (int)count;
         return SPHB200_OK;
     }
 
@@ -403,7 +454,9 @@ class Sim final : public sphb200_sim {
                  uint64_t *grp, int64_t *cells) override {
         if (!uploaded) return fail(SPHB200_ESTATE, "download before upload");
         CK(cudaSetDevice(device));
-        const int64_t cnt = n;
+        // slab mode: only the owned range [own_p0, own_p1) of the table is this rank's to report
+        const int64_t off = slab.active ? slab.own_p0 : 0;
+        const int64_t cnt = slab.active ? slab.own_p1 - slab.own_p0 : n;
         unsigned char *sp = stage.p;
         size_t vb = (size_t)cnt * D * sizeof(T), sb = (size_t)cnt * sizeof(T);
         T *d_pos = (T *)sp; sp += vb;
@@ -412,11 +465,12 @@ class Sim final : public sphb200_sim {
         sp += vb;
         T *d_rho = (T *)sp; sp += sb;
         T *d_pr = (T *)sp; sp += sb;
-        k_unpack_download<T, D><<<grid_for(cnt), 256, 0, stream>>>((int)cnt, A.p, B.p, acc.p, d_pos, d_vel, d_acc, d_rho, d_pr);
+        k_unpack_download<T, D><<<grid_for(cnt), 256, 0, stream>>>((int)cnt, A.p + off, B.p + off, acc.p + off, d_pos, d_vel, d_acc,
+                                                                  d_rho, d_pr);
         ++launches;
         CK(cudaGetLastError());
         std::vector<long long> hid((size_t)cnt);
-        CK(cudaMemcpyAsync(hid.data(), id.p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(hid.data(), id.p + off, (size_t)cnt * 8, cudaMemcpyDeviceToHost, stream));
         std::vector<T> hv;
         std::vector<int64_t> order_idx;
         CK(cudaStreamSynchronize(stream));
@@ -446,16 +500,16 @@ class Sim final : public sphb200_sim {
         if ((rc = fetch(accel, d_acc, sizeof(T), D))) return rc;
         if ((rc = fetch(rho, d_rho, sizeof(T), 1))) return rc;
         if ((rc = fetch(press, d_pr, sizeof(T), 1))) return rc;
-        if ((rc = fetch(ids, id.p, 8, 1))) return rc;
-        if ((rc = fetch(ty, type.p, 1, 1))) return rc;
-        if ((rc = fetch(grp, group.p, 8, 1))) return rc;
+        if ((rc = fetch(ids, id.p + off, 8, 1))) return rc;
+        if ((rc = fetch(ty, type.p + off, 1, 1))) return rc;
+        if ((rc = fetch(grp, group.p + off, 8, 1))) return rc;
         if (cells) {
             // Cells field = CartesianIndex assigned at the last UpdateNeighbors! (stale in between)
             std::vector<int> hk((size_t)cnt);
             if (!have_cells) {
                 memset(cells, 0, (size_t)cnt * D * 8);
             } else {
-                CK(cudaMemcpyAsync(hk.data(), ckey.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, stream));
+                CK(cudaMemcpyAsync(hk.data(), ckey.p + off, (size_t)cnt * 4, cudaMemcpyDeviceToHost, stream));
                 CK(cudaMemcpyAsync(h_grid, d_grid.p, sizeof(GridInfo), cudaMemcpyDeviceToHost, stream));
                 CK(cudaStreamSynchronize(stream));
                 for (int64_t k = 0; k < cnt; ++k) {
@@ -476,7 +530,7 @@ class Sim final : public sphb200_sim {
         if (D == 3) c[am.ax_m] = cm + h_grid->cmin[am.ax_m];
         c[am.ax_s] = cs + h_grid->cmin[am.ax_s];
     }
-    int64_t num_particles() const override { return n; }
+    int64_t num_particles() const override { return slab.active ? slab.own_p1 - slab.own_p0 : n; }
     int64_t launch_count() const override { return launches; }
 
     int sync_ctl() {
@@ -505,7 +559,7 @@ class Sim final : public sphb200_sim {
         rep->iteration = h_ctl->iteration;
         rep->index_counter = 0;
         rep->n_rebuilds = h_ctl->n_rebuilds;
-        rep->n_particles = slab.active ? (int64_t)(h_grid->own_p1 - h_grid->own_p0) : n;
+        rep->n_particles = slab.active ? (int64_t)(slab.own_p1 - slab.own_p0) : n;
         rep->n_halo = slab.active ? n - rep->n_particles : 0;
         rep->total_time = h_ctl->total_time;
         rep->current_dt = h_ctl->current_dt;
@@ -534,18 +588,19 @@ class Sim final : public sphb200_sim {
         t.ghost = prm.mdbc ? (scratch ? ghost2.p : ghost.p) : nullptr;
         t.id = scratch ? id2.p : id.p;
         t.group = scratch ? group2.p : group.p;
+        t.okey = scratch ? okey2.p : okey.p;
         t.type = scratch ? type2.p : type.p;
         t.ckey = scratch ? ckey2.p : ckey.p;
         return t;
     }
 
     // UpdateNeighbors! — every kernel is predicated on ctl->do_rebuild
-    int enqueue_rebuild() {
+    int enqueue_rebuild(const SlabFilter &flt = SlabFilter{0, 0, 0, 0, 0, 0}, int count_rebuild = 1) {
         const int nn = (int)n;
         const int gp = grid_for(nn);
         const int gc = grid_for(cell_cap);
         const int nscan = (int)(cell_cap / SCAN_CHUNK + 1);
-        k_cell_bbox<T, D><<<gp, 256, 0, stream>>>(A.p, nn, prm.H_inv, ccoord.p, d_ctl.p, d_grid.p);
+        k_cell_bbox<T, D><<<gp, 256, 0, stream>>>(A.p, nn, prm.H_inv, ccoord.p, d_ctl.p, d_grid.p, am, flt);
         k_grid_setup<D><<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, am, cell_cap, row_cap, own_lo, own_hi);
         k_zero_counts<<<gc, 256, 0, stream>>>(d_ctl.p, d_grid.p, cell_count.p);
         k_cell_count<D><<<gp, 256, 0, stream>>>(ccoord.p, nn, am, d_ctl.p, d_grid.p, key_tmp.p, slot_tmp.p, cell_count.p);
@@ -553,10 +608,11 @@ class Sim final : public sphb200_sim {
         k_scan_top<<<1, 1024, 0, stream>>>(d_ctl.p, d_grid.p, scan_partial.p);
         k_scan_final<<<nscan, SCAN_THREADS, 0, stream>>>(d_ctl.p, d_grid.p, cell_count.p, scan_partial.p, cell_start.p);
         k_scatter_unstable<<<gp, 256, 0, stream>>>(d_ctl.p, key_tmp.p, slot_tmp.p, nn, cell_start.p, tmp_idx.p);
-        k_stable_rank<<<gp, 256, 0, stream>>>(d_ctl.p, key_tmp.p, tmp_idx.p, nn, cell_start.p, perm.p);
-        k_gather_table<T, D><<<gp, 256, 0, stream>>>(d_ctl.p, perm.p, nn, table(false), table(true), key_tmp.p);
-        k_copy_table<T, D><<<gp, 256, 0, stream>>>(d_ctl.p, nn, table(true), table(false));
-        k_build_bricks<<<1, 256, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, BT, bricks.p, brick_cap, nn);
+        k_stable_rank<<<gp, 256, 0, stream>>>(d_ctl.p, d_grid.p, key_tmp.p, tmp_idx.p, nn, cell_start.p, okey.p, perm.p);
+        k_gather_table<T, D><<<gp, 256, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, perm.p, table(false), table(true), key_tmp.p,
+                                                     ccoord.p);
+        k_copy_table<T, D><<<gp, 256, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, table(true), table(false));
+        k_build_bricks<<<1, 256, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, BT, bricks.p, brick_cap, count_rebuild);
         k_finish_rebuild<<<1, 1, 0, stream>>>(d_ctl.p);
         launches += 13;
         CK(cudaGetLastError());
@@ -655,11 +711,11 @@ class Sim final : public sphb200_sim {
 
     // phase A of one step: S0, S1 and the S2 decision
     int enqueue_step_head() {
-        const int nn = (int)n;
-        k_reduce_dt_dx<T, D><<<grid_for(nn), 256, 0, stream>>>(A.p, B.p, Ah.p, acc.p, 0, nn, ph.h, ph.eta2, have_half ? 1 : 0,
-                                                               d_ctl.p);
-        int rc = slab.allreduce_ctl(this, d_ctl.p, stream);
-        if (rc) return rc;
+        const int p0 = slab.active ? slab.own_p0 : 0, p1 = slab.active ? slab.own_p1 : (int)n;
+        k_reduce_dt_dx<T, D><<<grid_for(p1 - p0), 256, 0, stream>>>(A.p, B.p, Ah.p, acc.p, p0, p1, ph.h, ph.eta2, have_half ? 1 : 0,
+                                                                    d_ctl.p);
+        int rc;
+        if (slab.active && (rc = slab_allreduce_ctl())) return rc;
         k_step_control<T><<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, ph.h, ph.c0, (T)prm.cfl);
         launches += 2;
         CK(cudaGetLastError());
@@ -730,6 +786,12 @@ class Sim final : public sphb200_sim {
         return SPHB200_OK;
     }
     int run_steps_slab(int64_t nsteps, bool until_target);
+    int slab_exchange_counts(int to_left, int to_right, int *from_left, int *from_right);
+    int slab_exchange_records(Table<T, D> from, int sl0, int nl, int sr0, int nr, int dst0, int rl, int rr);
+    int slab_exchange_halo(TA *a, TB *b);
+    int slab_allreduce_ctl();
+    int slab_sort(const SlabFilter &flt, int count_rebuild);
+    int slab_rebuild();
 
     int step(int64_t nsteps, int reset_dx, sphb200_report *rep) override {
         if (!uploaded) return fail(SPHB200_ESTATE, "step before upload");
@@ -993,6 +1055,7 @@ class Sim final : public sphb200_sim {
     // reference's TimerOutputs labels "01", "02", "05/06", "08-11" (src/SPHCellList.jl:748-800)
     int stage_times(double *ms_out, int cnt) override {
         if (!uploaded || !have_cells) return fail(SPHB200_ESTATE, "stage_times needs a running simulation");
+        if (slab.active) return fail(SPHB200_ESTATE, "stage-level calls are single-GPU only");
         CK(cudaSetDevice(device));
         cudaEvent_t ev[6];
         for (auto &e : ev) CK(cudaEventCreate(&e));

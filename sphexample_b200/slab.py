@@ -1,0 +1,128 @@
+"""Host side of the multi-GPU slab decomposition (one process per GPU).
+
+The reference is single-process; this module is the launch-side plumbing only:
+choose slab edges on cell-layer boundaries so that every rank owns about the same number of
+particles, hand each rank its particles, and bootstrap the library's NCCL communicator by
+broadcasting the unique id with `torch.distributed`.  Halo exchange, migration and the Δt
+all-reduce run inside libsphb200 (csrc/sph_slab*.cuh).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+INT64_MIN, INT64_MAX = -(2 ** 63), 2 ** 63 - 1
+
+
+def cell_coord(x: np.ndarray, H_inv: float) -> np.ndarray:
+    """map_floor of the reference (src/SPHCellList.jl:56-61): sign(x)·trunc(|x|·H⁻¹ + ½)."""
+    x = np.asarray(x, np.float64)
+    return (np.sign(x) * np.trunc(np.abs(x) * H_inv + 0.5)).astype(np.int64)
+
+
+def plan_edges(coords: np.ndarray, world: int, min_width: int = 2) -> List[int]:
+    """Slab edges e[0] < e[1] < ... < e[world] on cell-layer boundaries; rank r owns layers
+    e[r] <= c < e[r+1].  Edges follow the particle-count prefix sum over layers (equal-width
+    slabs are unusable for a dam break: the water starts in one corner of the tank), subject to
+    every slab being at least `min_width` layers wide (the exchange protocol needs 2)."""
+    coords = np.asarray(coords, np.int64)
+    cmin, cmax = int(coords.min()), int(coords.max())
+    nlay = cmax - cmin + 1
+    if nlay < world * min_width:
+        raise ValueError(f"{nlay} cell layers along the slab axis cannot feed {world} ranks of >= {min_width} layers")
+    hist = np.bincount(coords - cmin, minlength=nlay)
+    cum = np.concatenate([[0], np.cumsum(hist)])          # cum[k] = particles in layers < k
+    total = cum[-1]
+    edges = [0]
+    for r in range(1, world):
+        k = int(np.searchsorted(cum, total * r / world, side="left"))
+        # choose the closer of the two layer boundaries around the quantile
+        if k > 0 and abs(cum[k - 1] - total * r / world) <= abs(cum[min(k, nlay)] - total * r / world):
+            k -= 1
+        k = max(k, edges[-1] + min_width)
+        k = min(k, nlay - (world - r) * min_width)
+        edges.append(k)
+    edges.append(nlay)
+    return [cmin + e for e in edges]
+
+
+def owner_of(coords: np.ndarray, edges: Sequence[int]) -> np.ndarray:
+    """rank index of every particle (layers outside the planned range go to the end ranks)."""
+    inner = np.asarray(edges[1:-1], np.int64)
+    return np.searchsorted(inner, np.asarray(coords, np.int64), side="right")
+
+
+def slab_bounds(edges: Sequence[int], rank: int):
+    world = len(edges) - 1
+    lo = INT64_MIN if rank == 0 else int(edges[rank])
+    hi = INT64_MAX if rank == world - 1 else int(edges[rank + 1])
+    return lo, hi
+
+
+def best_axis(positions: np.ndarray, H_inv: float, world: int) -> int:
+    """Slab axis among 1..D-1 (x stays the fastest key component): the one whose balanced split
+    has the smallest halo, i.e. the most layers per rank."""
+    D = positions.shape[1]
+    best, best_layers = 1, -1
+    for ax in range(1, D):
+        c = cell_coord(positions[:, ax], H_inv)
+        layers = int(c.max() - c.min() + 1)
+        if layers > best_layers:
+            best, best_layers = ax, layers
+    return best
+
+
+class SlabDecomposition:
+    """Distribute one particle table over `world` ranks and join the library communicator.
+
+        dec = SlabDecomposition(sim, particles, H_inv, rank, world, axis=1); dec.setup()
+        sim.step(...)                       # collective: every rank calls it
+        state = dec.gather(order="id")      # rank 0 gets the whole table back
+    """
+
+    def __init__(self, sim, particles, H_inv: float, rank: int, world: int, axis: Optional[int] = None,
+                 edges: Optional[Sequence[int]] = None):
+        self.sim, self.parts, self.H_inv, self.rank, self.world = sim, particles, float(H_inv), rank, world
+        pos = np.asarray(particles.Position)
+        self.axis = best_axis(pos, self.H_inv, world) if axis is None else int(axis)
+        self.coords = cell_coord(pos[:, self.axis], self.H_inv)
+        self.edges = list(edges) if edges is not None else plan_edges(self.coords, world)
+        self.mine = np.nonzero(owner_of(self.coords, self.edges) == rank)[0]
+        self.n_owned = int(self.mine.size)
+
+    def broadcast_unique_id(self) -> bytes:
+        import torch
+        import torch.distributed as dist
+        from .simulation import comm_unique_id
+        if self.world == 1 and not dist.is_initialized():
+            return comm_unique_id()
+        box = [comm_unique_id() if self.rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, device=torch.device("cuda", torch.cuda.current_device())
+                                   if dist.get_backend() == "nccl" else None)
+        return box[0]
+
+    def setup(self):
+        uid = self.broadcast_unique_id()
+        self.sim.comm_init(uid, self.rank, self.world, self.axis)
+        lo, hi = slab_bounds(self.edges, self.rank)
+        self.sim.set_slab(lo, hi)
+        self.sim.upload(self.parts.permuted(self.mine))
+        return self
+
+    def gather(self, order: str = "id", fields=("Position", "Velocity", "Density", "Pressure", "ID")):
+        """All ranks' owned particles on rank 0 (None elsewhere)."""
+        import torch.distributed as dist
+        st = self.sim.download(fields=fields)
+        if self.world == 1:
+            parts = [st]
+        else:
+            parts = [None] * self.world if self.rank == 0 else None
+            dist.gather_object(st, parts, dst=0)
+            if self.rank != 0:
+                return None
+        out = {k: np.concatenate([p[k] for p in parts]) for k in fields}
+        if order == "id":
+            o = np.argsort(out["ID"], kind="stable")
+            out = {k: v[o] for k, v in out.items()}
+        return out
