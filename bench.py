@@ -28,6 +28,7 @@ if ROOT not in sys.path:
 METRIC = "Mparticle-updates/s (3D dam-break)"
 UNIT = "Mparticle-updates/s"
 PER_GPU_PARTICLES = 1_000_000
+SLAB_AXIS = 1   # y: the dam break is (nearly) uniform along y, so y-slabs stay balanced through the run
 
 
 def build_case(n_target, float_type="float32"):
@@ -165,6 +166,7 @@ def run_ours(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libsphb200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    dist = torch.distributed if world > 1 else None
     n_total = PER_GPU_PARTICLES * world
     if args.particles:
         n_total = int(args.particles)
@@ -175,26 +177,47 @@ def run_ours(args, rank, world, local_rank):
     sim = Simulation(p, device=local_rank)
     stream = torch.cuda.current_stream()
     sim.set_stream(stream.cuda_stream)
+    dec = None
     if world > 1:
         from sphexample_b200 import slab
-        dec = slab.SlabDecomposition(sim, parts, case, rank, world)
-        dec.setup()
-        n_local = dec.n_owned
+        dec = slab.SlabDecomposition(sim, parts, p.H_inv, rank, world, axis=SLAB_AXIS)
+        dec.join()
+        mine = dec.mine
     else:
-        # pinned host copies of the caller's arrays (the reference-facing call takes host buffers)
-        host = {k: torch.from_numpy(np.ascontiguousarray(getattr(parts, k))).pin_memory().numpy()
-                for k in ("Position", "Velocity", "Density")}
-        types = np.ascontiguousarray(parts.Type, np.uint8)
-        sim.upload_arrays(host["Position"], host["Velocity"], host["Density"], types)
-        n_local = n
+        mine = slice(None)
+    # pinned host copies of this rank's part of the caller's table (the reference-facing call takes host buffers)
+    host = {k: torch.from_numpy(np.ascontiguousarray(getattr(parts, k)[mine])).pin_memory().numpy()
+            for k in ("Position", "Velocity", "Density")}
+    types = np.ascontiguousarray(parts.Type[mine], np.uint8)
+    ids = np.ascontiguousarray(parts.ID[mine], np.int64)
+    n_local = int(types.shape[0])
+
+    def upload():
+        sim.upload_arrays(host["Position"], host["Velocity"], host["Density"], types, ids=ids)
 
     def barrier():
         if world > 1:
-            torch.distributed.barrier()
+            dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor(list(vals), device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return int(v)
+        t = torch.tensor([int(v)], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        return int(t.item())
+
+    upload()
     # ---- warm-up -------------------------------------------------------------------------------
-    sim.step(max(args.warmup, 3), reset_delta_x=True)
+    warm = max(args.warmup, 3)
+    sim.step(warm, reset_delta_x=True)
     barrier()
     # ---- timed region: exactly K steps, device events, max over ranks --------------------------
     sampler = ClockSampler(local_rank)
@@ -219,7 +242,8 @@ def run_ours(args, rank, world, local_rank):
     t1 = time.time()
     ms = float(sum(a.elapsed_time(b) for a, b in ev))
     launches = sim.launch_count - l0
-    # back-to-back (warm L2, one host sync per 64 steps): what a production run sees
+    rebuilds_timed = int(rep["n_rebuilds"])
+    # back-to-back (warm L2, one host sync per 64 steps on one GPU): what a production run sees
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -227,13 +251,8 @@ def run_ours(args, rank, world, local_rank):
     e1.record(stream)
     barrier()
     ms_b2b = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms, ms_b2b], device="cuda")
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms, ms_b2b = float(t[0].item()), float(t[1].item())
-        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
-        torch.distributed.all_reduce(lt)
-        launches = int(lt.item())
+    ms, ms_b2b = max_over_ranks([ms, ms_b2b])
+    launches = sum_over_ranks(launches)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     value = n * args.steps / (ms * 1e-3) / 1e6
 
@@ -242,87 +261,103 @@ def run_ours(args, rank, world, local_rank):
     reps = 5
     for _ in range(reps):
         flush.zero_()
-        stage += np.array(sim.stage_times()) if world == 1 else np.zeros(5)
-    stage /= reps
-    line = None
+        stage += np.array(sim.stage_times())
+    stage = np.array(max_over_ranks(stage / reps))
+    n_local_max = int(max_over_ranks([sim.report()["n_particles"]])[0])
+    D, sz = 3, 4
+    bytes_pass0 = n_local_max * (4 * D + 4) * sz          # read x,v,rho,P ; write x_h,v_h,rho_h,P_h
+    bytes_pass1 = n_local_max * (7 * D + 5) * sz          # read half state + own state n + rho_n ; write x,v,rho,P,a
+    peak, how = measured_peaks()
+    t_avg = 0.5 * (stage[2] + stage[3]) * 1e-3
+    achieved = 0.5 * (bytes_pass0 + bytes_pass1) / t_avg / 1e9
+    prof = os.path.join(ROOT, "profiles", "interact_traffic.json")
+    traffic = json.load(open(prof)).get("dram_bytes_per_launch") if os.path.exists(prof) else None
+    roof = {"bound": "hbm", "kernel": "k_interact<float,3,PASS,...> (avg of the two passes of a step, slowest rank)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "peak_source": how, "algorithmic_bytes_per_launch": 0.5 * (bytes_pass0 + bytes_pass1),
+            "avg_launch_ms": 0.5 * (stage[2] + stage[3]),
+            "note": "compute-bound kernel (~18 kflop per particle per pass on the fp32 pipe, SURVEY 8d): "
+                    "the HBM fraction is reported because the metric asks for it",
+            "stage_ms": {"reduce_control": stage[0], "rebuild_predicated": stage[1], "pass0_fused": stage[2],
+                         "pass1_fused": stage[3], ("metadata" if world == 1 else "halo_exchanges"): stage[4]}}
+
+    # ---- end to end through the reference-facing call with HOST buffers -------------------------
+    cap = n_local + n_local // 8 + 1024            # owned counts drift a little with migration
+    out = {k: torch.empty((cap,) + v.shape[1:], dtype=torch.float32).pin_memory().numpy() for k, v in
+           (("Position", host["Position"]), ("Velocity", host["Velocity"]), ("Density", host["Density"]),
+            ("Pressure", host["Density"]))}
+    iters = 2
+    barrier()
+    e0.record(stream)
+    for _ in range(iters):
+        upload()
+        sim.step(args.steps, reset_delta_x=True)
+        sim.download_into(out["Position"][:sim.num_particles], out["Velocity"][:sim.num_particles],
+                          out["Density"][:sim.num_particles], out["Pressure"][:sim.num_particles])
+    e1.record(stream)
+    barrier()
+    ems = max_over_ranks([e0.elapsed_time(e1)])[0]
+    h2d = sum_over_ranks(sum(host[k].nbytes for k in host) + types.nbytes + ids.nbytes)
+    d2h = sum_over_ranks(sum(v[:sim.num_particles].nbytes for v in out.values()))
+    e2e = {"value": n * args.steps * iters / (ems * 1e-3) / 1e6, "unit": UNIT,
+           "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+           "definition": f"one SimulationLoop-style call per output interval: upload host particle table "
+                         f"({h2d} B, pinned) -> {args.steps} steps -> download x,v,rho,P ({d2h} B); "
+                         f"bytes amortised per step, all ranks"}
+    # worst case for context: a host round trip around EVERY step
+    k2 = 5
+    barrier()
+    e0.record(stream)
+    for _ in range(k2):
+        upload()
+        sim.step(1, reset_delta_x=True)
+        sim.download_into(out["Position"][:sim.num_particles], out["Velocity"][:sim.num_particles],
+                          out["Density"][:sim.num_particles], out["Pressure"][:sim.num_particles])
+    e1.record(stream)
+    barrier()
+    e2e["roundtrip_every_step_value"] = n * k2 / (max_over_ranks([e0.elapsed_time(e1)])[0] * 1e-3) / 1e6
+
     if rank == 0:
-        D, sz = 3, 4
-        bytes_pass0 = n_local * (4 * D + 4) * sz          # read x,v,rho,P ; write x_h,v_h,rho_h,P_h
-        bytes_pass1 = n_local * (7 * D + 5) * sz          # read half state + own state n + rho_n ; write x,v,rho,P,a
-        peak, how = measured_peaks()
-        roof = None
-        if world == 1 and stage[2] > 0 and stage[3] > 0:
-            t_avg = 0.5 * (stage[2] + stage[3]) * 1e-3
-            achieved = 0.5 * (bytes_pass0 + bytes_pass1) / t_avg / 1e9
-            prof = os.path.join(ROOT, "profiles", "interact_traffic.json")
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch") if os.path.exists(prof) else None
-            roof = {"bound": "hbm", "kernel": "k_interact<float,3,PASS,fast,compact> (avg of the two passes of a step)",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "peak_source": how, "algorithmic_bytes_per_launch": 0.5 * (bytes_pass0 + bytes_pass1),
-                    "avg_launch_ms": 0.5 * (stage[2] + stage[3]),
-                    "note": "compute-bound kernel (~18 kflop per particle per pass on the fp32 pipe, SURVEY 8d): "
-                            "the HBM fraction is reported because the metric asks for it",
-                    "stage_ms": {"reduce_control": stage[0], "rebuild_predicated": stage[1], "pass0_fused": stage[2],
-                                 "pass1_fused": stage[3], "metadata": stage[4]}}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(n, world), "clocks": clocks,
-                "gpu_launches": int(launches), "roofline": roof,
-                "rebuilds_in_timed_region": None, "dp": dp,
+                "gpu_launches": int(launches), "roofline": roof, "e2e": e2e,
+                "rebuilds_in_timed_region": rebuilds_timed, "dp": dp,
                 "back_to_back": {"value": n * args.steps / (ms_b2b * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_b2b / args.steps,
-                                 "note": "same K steps enqueued back to back, warm L2, one host sync per 64 steps"}}
-
-    # ---- end to end through the reference-facing call with HOST buffers (N = 1) -----------------
-    if world == 1:
-        out = {k: torch.empty(v.shape, dtype=torch.float32).pin_memory().numpy() for k, v in
-               (("Position", host["Position"]), ("Velocity", host["Velocity"]), ("Density", host["Density"]),
-                ("Pressure", host["Density"]))}
-        iters = 2
-        torch.cuda.synchronize()
-        e0.record(stream)
-        for _ in range(iters):
-            sim.upload_arrays(host["Position"], host["Velocity"], host["Density"], types)
-            sim.step(args.steps, reset_delta_x=True)
-            sim.download_into(out["Position"], out["Velocity"], out["Density"], out["Pressure"])
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ems = e0.elapsed_time(e1)
-        h2d = sum(host[k].nbytes for k in host) + types.nbytes
-        d2h = sum(v.nbytes for v in out.values())
-        line["e2e"] = {"value": n * args.steps * iters / (ems * 1e-3) / 1e6, "unit": UNIT,
-                       "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
-                       "definition": f"one SimulationLoop-style call per output interval: upload host particle table "
-                                     f"({h2d} B, pinned) -> {args.steps} steps -> download x,v,rho,P ({d2h} B); "
-                                     f"bytes amortised per step"}
-        # worst case for context: a host round trip around EVERY step
-        k2 = 5
-        e0.record(stream)
-        for _ in range(k2):
-            sim.upload_arrays(host["Position"], host["Velocity"], host["Density"], types)
-            sim.step(1, reset_delta_x=True)
-            sim.download_into(out["Position"], out["Velocity"], out["Density"], out["Pressure"])
-        e1.record(stream)
-        torch.cuda.synchronize()
-        line["e2e"]["roundtrip_every_step_value"] = n * k2 / (e0.elapsed_time(e1) * 1e-3) / 1e6
-        # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N = 1 only -----------------
-        try:
-            from oracle import oracle as orc
-            orc.build()
-            threads = orc.max_threads()
-            cal_case, cal_dp = build_case(int(os.environ.get("SPHB200_CPU_SAMPLE", "250000")), "float64")
-            rate, secs = cpu_port_rate(cal_case, threads, steps=3)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{len(cal_case.particles)} particles (dp={cal_dp}) of the same 3D dam break, "
-                                              f"3 steps after 1 warm-up step incl. rebuild, fp64, {secs:.1f} s"}
-        except Exception as ex:   # the checker failing must not void the GPU number
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
-    elif rank == 0:
-        line["e2e"] = None
-    full = sim.report()
-    if rank == 0:
-        line["rebuilds_in_timed_region"] = None if rep is None else int(rep["n_rebuilds"])
+                                 "note": "same K steps enqueued back to back, warm L2"}}
+        if world > 1:
+            line["slab"] = {"axis": "xyz"[SLAB_AXIS], "edges": [int(e) for e in dec.edges],
+                            "owned_max": n_local_max, "owned_mean": n / world}
+        # ---- CPU baseline (oracle port) on a bounded sample of the same workload, N = 1 only ----
+        if world == 1:
+            try:
+                line["cpu_baseline"] = cpu_baseline_sample(n_total)
+            except Exception as ex:   # the checker failing must not void the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
         print(json.dumps(line), flush=True)
     sim.close()
+
+
+def cpu_baseline_sample(n_total, budget_s=None):
+    """the oracle port on all host threads: the SAME workload, a bounded number of steps (~15 s)"""
+    from oracle import oracle as orc
+    orc.build()
+    threads = orc.max_threads()
+    budget_s = float(os.environ.get("SPHB200_CPU_BUDGET_S", "15")) if budget_s is None else budget_s
+    case, dp = build_case(n_total, "float64")
+    o = orc.Oracle(params_of(case), case.particles, nthreads=threads)
+    t0 = time.perf_counter()
+    o.step(1, True)                        # warm-up step incl. the first rebuild
+    t_first = time.perf_counter() - t0
+    steps = int(max(2, min(50, budget_s / max(t_first, 1e-3))))
+    t0 = time.perf_counter()
+    o.step(steps, False)
+    secs = time.perf_counter() - t0
+    npart = len(case.particles)
+    o.close()
+    return {"value": npart * steps / secs / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{steps} steps (after 1 warm-up step incl. rebuild) of the same {npart}-particle workload "
+                      f"(dp={dp}), fp64, {secs:.1f} s on {threads} host threads"}
 
 
 def main():

@@ -289,34 +289,83 @@ int Sim<T, D>::slab_rebuild() {
     return SPHB200_OK;
 }
 
+// S2 .. S19 of one step in slab mode (after the head has been synchronised); ev: optional 6 events
+// bracketing rebuild+motion+snapshots | pass 0 | halo n+1/2 | pass 1 | halo n+1
+template <class T, int D>
+int Sim<T, D>::slab_step_body(cudaEvent_t *ev) {
+    int rc;
+#define EV(k) if (ev) CKS(cudaEventRecord(ev[k], stream))
+    EV(0);
+    if (h_ctl->do_rebuild && (rc = slab_rebuild())) return rc;
+    if ((rc = enqueue_motion(-1.0))) return rc;                       // S3
+    if ((rc = enqueue_snapshots())) return rc;
+    EV(1);
+    if ((rc = launch_interact(0, EPI_FUSED))) return rc;              // S4-S10, S13 (owned bricks)
+    if ((rc = enqueue_motion(-1.0))) return rc;                       // S12
+    EV(2);
+    if ((rc = slab_exchange_halo(Ah.p, Bh.p))) return rc;             // state n+1/2 of the halo layers
+    EV(3);
+    if ((rc = launch_interact(1, EPI_FUSED))) return rc;              // S11, S14-S18
+    k_step_end<<<1, 1, 0, stream>>>(d_ctl.p);                         // S19
+    ++launches;
+    EV(4);
+    if ((rc = slab_exchange_halo(A.p, B.p))) return rc;               // state n+1 of the halo layers
+    EV(5);
+#undef EV
+    have_half = true;
+    have_cells = true;
+    return SPHB200_OK;
+}
+
+template <class T, int D>
+int Sim<T, D>::slab_check_head(bool *stop, bool until_target) {
+    int rc;
+    if ((rc = enqueue_step_head())) return rc;
+    if ((rc = sync_ctl())) return rc;
+    if (h_ctl->error == SPHB200_ENUMERIC)
+        return fail(SPHB200_ENUMERIC, "non-finite state or time step at iteration %lld (t = %g)", h_ctl->iteration, h_ctl->total_time);
+    if (h_ctl->error) return fail(h_ctl->error, "device reported error %d (rank %d)", h_ctl->error, slab.rank);
+    *stop = until_target && h_ctl->done;
+    return SPHB200_OK;
+}
+
 template <class T, int D>
 int Sim<T, D>::run_steps_slab(int64_t nsteps, bool until_target) {
     int rc = sync_ctl();
     if (rc) return rc;
     int64_t done_steps = 0;
     while (until_target || done_steps < nsteps) {
-        if ((rc = enqueue_step_head())) return rc;
-        if ((rc = sync_ctl())) return rc;
-        if (h_ctl->error == SPHB200_ENUMERIC)
-            return fail(SPHB200_ENUMERIC, "non-finite state or time step at iteration %lld (t = %g)", h_ctl->iteration, h_ctl->total_time);
-        if (h_ctl->error) return fail(h_ctl->error, "device reported error %d (rank %d)", h_ctl->error, slab.rank);
-        if (until_target && h_ctl->done) break;
-        if (h_ctl->do_rebuild && (rc = slab_rebuild())) return rc;
-        if ((rc = enqueue_motion(-1.0))) return rc;                       // S3
-        if ((rc = enqueue_snapshots())) return rc;
-        if ((rc = launch_interact(0, EPI_FUSED))) return rc;              // S4-S10, S13 (owned bricks)
-        if ((rc = enqueue_motion(-1.0))) return rc;                       // S12
-        if ((rc = slab_exchange_halo(Ah.p, Bh.p))) return rc;             // state n+½ of the halo layers
-        if ((rc = launch_interact(1, EPI_FUSED))) return rc;              // S11, S14-S18
-        k_step_end<<<1, 1, 0, stream>>>(d_ctl.p);                         // S19
-        ++launches;
-        if ((rc = slab_exchange_halo(A.p, B.p))) return rc;               // state n+1 of the halo layers
-        have_half = true;
-        have_cells = true;
+        bool stop = false;
+        if ((rc = slab_check_head(&stop, until_target))) return rc;
+        if (stop) break;
+        if ((rc = slab_step_body(nullptr))) return rc;
         ++done_steps;
     }
     if ((rc = sync_ctl())) return rc;
     if (h_ctl->error) return fail(h_ctl->error, "device reported error %d (rank %d)", h_ctl->error, slab.rank);
+    return SPHB200_OK;
+}
+
+// slab-mode stage times of ONE extra step (collective): [0] reductions + all-reduce + control,
+// [1] rebuild + motion + snapshots, [2] pass 0, [3] pass 1, [4] the two halo exchanges
+template <class T, int D>
+int Sim<T, D>::slab_stage_times(double *ms_out, int cnt) {
+    cudaEvent_t ev[7];
+    for (auto &e : ev) CKS(cudaEventCreate(&e));
+    CKS(cudaEventRecord(ev[6], stream));
+    bool stop = false;
+    int rc = slab_check_head(&stop, false);
+    if (rc) return rc;
+    if ((rc = slab_step_body(ev))) return rc;
+    CKS(cudaStreamSynchronize(stream));
+    float t[6];
+    CKS(cudaEventElapsedTime(&t[0], ev[6], ev[0]));
+    for (int k = 0; k < 5; ++k) CKS(cudaEventElapsedTime(&t[k + 1], ev[k], ev[k + 1]));
+    double out[5] = {t[0], t[1], t[2], t[4], (double)t[3] + t[5]};
+    for (int k = 0; k < 5 && k < cnt; ++k) ms_out[k] = out[k];
+    for (auto &e : ev) cudaEventDestroy(e);
+    if ((rc = sync_ctl())) return rc;
+    if (h_ctl->error) return fail(h_ctl->error, "device reported error %d", h_ctl->error);
     return SPHB200_OK;
 }
 

@@ -792,6 +792,9 @@ class Sim final : public sphb200_sim {
     int slab_allreduce_ctl();
     int slab_sort(const SlabFilter &flt, int count_rebuild);
     int slab_rebuild();
+    int slab_step_body(cudaEvent_t *ev);
+    int slab_check_head(bool *stop, bool until_target);
+    int slab_stage_times(double *ms_out, int cnt);
 
     int step(int64_t nsteps, int reset_dx, sphb200_report *rep) override {
         if (!uploaded) return fail(SPHB200_ESTATE, "step before upload");
@@ -1055,8 +1058,8 @@ class Sim final : public sphb200_sim {
     // reference's TimerOutputs labels "01", "02", "05/06", "08-11" (src/SPHCellList.jl:748-800)
     int stage_times(double *ms_out, int cnt) override {
         if (!uploaded || !have_cells) return fail(SPHB200_ESTATE, "stage_times needs a running simulation");
-        if (slab.active) return fail(SPHB200_ESTATE, "stage-level calls are single-GPU only");
         CK(cudaSetDevice(device));
+        if (slab.active) return slab_stage_times(ms_out, cnt);
         cudaEvent_t ev[6];
         for (auto &e : ev) CK(cudaEventCreate(&e));
         int rc = 0;

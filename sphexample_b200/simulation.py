@@ -150,6 +150,11 @@ class Simulation:
         return list(ms)
 
     @property
+    def num_particles(self) -> int:
+        """particles this handle reports (slab mode: the owned ones)"""
+        return int(self._L.sphb200_num_particles(self._h))
+
+    @property
     def launch_count(self) -> int:
         return int(self._L.sphb200_launch_count(self._h))
 

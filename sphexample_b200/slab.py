@@ -102,11 +102,16 @@ class SlabDecomposition:
                                    if dist.get_backend() == "nccl" else None)
         return box[0]
 
-    def setup(self):
+    def join(self):
+        """communicator + slab bounds, no upload"""
         uid = self.broadcast_unique_id()
         self.sim.comm_init(uid, self.rank, self.world, self.axis)
         lo, hi = slab_bounds(self.edges, self.rank)
         self.sim.set_slab(lo, hi)
+        return self
+
+    def setup(self):
+        self.join()
         self.sim.upload(self.parts.permuted(self.mine))
         return self
 
