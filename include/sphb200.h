@@ -140,10 +140,15 @@ int64_t sphb200_launch_count(const sphb200_sim *sim);
 /* run all of this handle's work on the caller's CUDA stream (a cudaStream_t; NULL = the legacy
  * default stream) instead of the handle's own, so that the caller's CUDA events bracket it */
 int sphb200_set_stream(sphb200_sim *sim, void *cuda_stream);
-/* tuning knobs: "compact" (0/1 two-phase neighbour lists), "tma" (0/1 cp.async.bulk staging),
- * "smem_kb" (shared memory per CTA of the interaction kernel), "batch" (steps per host sync),
- * "generic" (1 = force the run-time-dispatched pair body) */
+/* tuning knobs: "compact" (0/1 two-phase walk of the cull kernel), "tma" (0/1 cp.async.bulk staging),
+ * "smem_kb" (shared memory per CTA of the cull kernel), "batch" (steps per host sync),
+ * "generic" (1 = force the run-time-dispatched pair body), "lists" (0/1 per-particle neighbour
+ * lists reused across passes), "skin" (list skin as a fraction of H), "lcap" (list entries per
+ * particle), "list_smem_kb" (shared memory per CTA of the list kernel) */
 int sphb200_set_option(sphb200_sim *sim, const char *name, double value);
+/* run-time counters: "list_builds", "list_off" (1 = lists switched off after an overflow),
+ * "halo_bytes_per_step", "migrated", "n_total" (owned + halo particles held) */
+int sphb200_get_stat(sphb200_sim *sim, const char *name, double *value);
 /* device time (ms) of the stages of ONE extra step, the analogue of the reference's TimerOutputs
  * sections (src/SPHCellList.jl:748-800): [0] Δt/Δx reductions + control ("01"), [1] neighbour
  * rebuild + motion + mDBC ("02"-"04"), [2] first NeighborLoop + half step ("05"-"07"),

@@ -126,6 +126,7 @@ __global__ void k_grid_setup(Ctl *ctl, GridInfo *grid, AxisMap am, long long cel
     grid->ns = ns;
     grid->ncell = (int)ncell;
     grid->nrows = (int)nrows;
+    grid->nbricks = 0;   // k_build_bricks appends
     // owned rows: slab coordinate c_s in [own_lo, own_hi)
     long long s0 = (long long)own_lo - grid->cmin[am.ax_s];
     long long s1 = (long long)own_hi - grid->cmin[am.ax_s];
@@ -361,59 +362,96 @@ __global__ void k_copy_table(const Ctl *ctl, const GridInfo *grid, const int *__
     }
 }
 
-// Brick list: every owned row (c_m, c_s) of cells is cut into segments of at most `bt`
-// consecutive particles; one brick is the unit of work of the interaction kernel.
-__global__ void k_build_bricks(Ctl *ctl, GridInfo *grid, const int *__restrict__ cell_start, int bt,
-                               Brick *__restrict__ bricks, int brick_cap, int count_rebuild) {
+// Brick list: every owned row (c_m, c_s) of cells is cut into segments of consecutive particles;
+// one brick is the unit of work of the interaction kernels.  A brick closes when it holds `bt`
+// particles (possibly in the middle of a cell) or when taking in the next cell would push its
+// candidate window — the particles of cells [first-1, last+1] of the 3^(D-1) neighbouring rows,
+// the thing the interaction kernels stage into shared memory — beyond `wlimit`.  The second rule
+// keeps sparse rows (two tank walls 100 cells apart in one row) from producing bricks whose
+// window spans the whole row.  One thread per row, two passes (count, write); bricks are appended
+// through an atomic counter, so their order (not their content) varies from run to run.
+template <int D>
+__global__ void k_build_bricks(Ctl *ctl, GridInfo *grid, const int *__restrict__ cell_start, int bt, int wlimit,
+                               Brick *__restrict__ bricks, int brick_cap) {
     if (ctl->error || ctl->done || !ctl->do_rebuild) return;
-    __shared__ int sw[33];
-    __shared__ int s_carry;
-    const int nx = grid->nx;
+    constexpr int NR = (D == 3) ? 9 : 3;
+    const int nx = grid->nx, nm = grid->nm;
     const int r0 = grid->own_row0, r1 = grid->own_row1;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (int rb = r0; rb < r1; rb += blockDim.x) {
-        int r = rb + threadIdx.x;
-        int p0 = 0, p1 = 0;
-        if (r < r1) {
-            p0 = cell_start[(size_t)r * nx];
-            p1 = cell_start[(size_t)(r + 1) * nx];
+    for (int r = r0 + blockIdx.x * blockDim.x + threadIdx.x; r < r1; r += gridDim.x * blockDim.x) {
+        const int rowbase = r * nx;
+        const int p0 = cell_start[rowbase], p1 = cell_start[rowbase + nx];
+        if (p1 <= p0) continue;
+        int roff[NR];
+#pragma unroll
+        for (int q = 0; q < NR; ++q) {
+            int dm = (D == 3) ? (q % 3 - 1) : 0;
+            int ds = (D == 3) ? (q / 3 - 1) : (q - 1);
+            roff[q] = rowbase + (ds * nm + dm) * nx;
         }
-        int nb = (p1 - p0 + bt - 1) / bt;
-        int total;
-        int off = block_exclusive_scan(nb, sw, total) + s_carry;
-        for (int k = 0; k < nb; ++k) {
-            if (off + k < brick_cap) {
-                Brick b;
-                b.t0 = p0 + k * bt;
-                b.t1 = min(p0 + (k + 1) * bt, p1);
-                bricks[off + k] = b;
+        int out = 0, nb = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) {
+                out = atomicAdd(&grid->nbricks, nb);
+                if (out + nb > brick_cap) {
+                    atomicCAS(&ctl->error, 0, SPH_ERR_ECAPACITY);
+                    break;
+                }
+            }
+            int t0 = p0, cfirst = -1, wlo = 0;
+            for (int cx = 1; cx < nx - 1; ++cx) {          // cells 0 and nx-1 are the empty padding
+                const int cs = cell_start[rowbase + cx], ce = cell_start[rowbase + cx + 1];
+                if (ce <= cs) continue;
+                if (cfirst < 0) {
+                    cfirst = cx;
+                    wlo = 0;
+#pragma unroll
+                    for (int q = 0; q < NR; ++q) wlo += cell_start[roff[q] + cx - 1];
+                } else {
+                    int whi = 0;
+#pragma unroll
+                    for (int q = 0; q < NR; ++q) whi += cell_start[roff[q] + cx + 2];
+                    if (whi - wlo > wlimit && cs > t0) {   // close before this cell
+                        if (pass) bricks[out++] = Brick{t0, cs};
+                        else ++nb;
+                        t0 = cs;
+                        cfirst = cx;
+                        wlo = 0;
+#pragma unroll
+                        for (int q = 0; q < NR; ++q) wlo += cell_start[roff[q] + cx - 1];
+                    }
+                }
+                while (ce - t0 >= bt) {                     // full bricks, possibly ending mid-cell
+                    if (pass) bricks[out++] = Brick{t0, t0 + bt};
+                    else ++nb;
+                    t0 += bt;
+                    cfirst = (t0 < ce) ? cx : -1;          // the next brick starts inside this cell, or afresh
+                    if (cfirst >= 0) {
+                        wlo = 0;
+#pragma unroll
+                        for (int q = 0; q < NR; ++q) wlo += cell_start[roff[q] + cx - 1];
+                    }
+                }
+            }
+            if (t0 < p1) {
+                if (pass) bricks[out++] = Brick{t0, p1};
+                else ++nb;
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) s_carry += total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        if (s_carry > brick_cap) {
-            ctl->error = SPH_ERR_ECAPACITY;
-            grid->nbricks = 0;
-        } else {
-            grid->nbricks = s_carry;
-        }
-        grid->own_p0 = cell_start[(size_t)r0 * nx];
-        grid->own_p1 = cell_start[(size_t)r1 * nx];
-        const int nm = grid->nm;
-        grid->own_l1 = cell_start[(size_t)min(r0 + nm, r1) * nx];
-        grid->own_l2 = cell_start[(size_t)max(r1 - nm, r0) * nx];
-        grid->n_total = cell_start[grid->ncell];
-        ctl->n_rebuilds += count_rebuild;
     }
 }
 
-// last kernel of the rebuild sequence: a successful rebuild clears the request
-__global__ void k_finish_rebuild(Ctl *ctl) {
-    if (ctl->error || ctl->done) return;
+// last kernel of the rebuild sequence: table layout for the slab exchange, and a successful
+// rebuild clears the request
+__global__ void k_finish_rebuild(Ctl *ctl, GridInfo *grid, const int *__restrict__ cell_start, int count_rebuild) {
+    if (ctl->error || ctl->done || !ctl->do_rebuild) return;
+    const int nx = grid->nx, nm = grid->nm;
+    const int r0 = grid->own_row0, r1 = grid->own_row1;
+    grid->own_p0 = cell_start[(size_t)r0 * nx];
+    grid->own_p1 = cell_start[(size_t)r1 * nx];
+    grid->own_l1 = cell_start[(size_t)min(r0 + nm, r1) * nx];
+    grid->own_l2 = cell_start[(size_t)max(r1 - nm, r0) * nx];
+    grid->n_total = cell_start[grid->ncell];
+    ctl->n_rebuilds += count_rebuild;
     ctl->do_rebuild = 0;
 }
 

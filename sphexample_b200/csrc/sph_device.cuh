@@ -88,8 +88,19 @@ struct Ctl {
     // reductions feeding Δt and Δx (bit patterns of non-negative reals, atomicMax-ed)
     unsigned long long red_disp2, red_visc, red_acc2;
     unsigned long long red_err;   // slab mode: max over ranks of -error (all-reduced with the three above)
+    unsigned long long red_vel2;  // max |v|² (bounds the displacement the neighbour lists have to absorb)
     // work distribution of the interaction kernel
-    int work_counter[2];
+    int work_counter[3];       // [0], [1]: the two passes; [2]: the list build
+    // per-particle neighbour lists (sph_interact.cuh): which kernel serves each pass of this step
+    int list_mode[2];          // LM_CULL / LM_USE
+    int list_build;            // this step starts with a list build (k_list_build)
+    int list_valid;            // lists exist for the current cell structure
+    int list_fail;             // a build overflowed: bit 0 candidates per brick window, bit 1 entries per particle
+    int list_fail_last;        // the reason of the most recent failed build (diagnostics)
+    int list_off;              // lists are switched off until the next cell rebuild (after a failed build)
+    int n_list_builds;
+    double list_move;          // bound on any particle's displacement since the last list build
+    double list_prev_vmax;     // max |v| at the previous step head
 };
 
 struct GridInfo {
@@ -134,6 +145,8 @@ __device__ __forceinline__ void mbar_fence_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// order earlier generic-proxy accesses to shared memory before later async-proxy (TMA) writes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }

@@ -176,7 +176,9 @@ SPH_HD FastTarget<T> make_fast_target(const Phys<T> &p, T rho, T P, T rhon, T ml
 // Divisions are restated as products with reciprocals (one per distinct denominator); on the
 // device the fp32 reciprocals and the square root are single MUFU approximations (1-2 ulp), the
 // fp64 ones stay IEEE divisions — see the tolerances in tests/test_gpu_parity.py.
-template <class T, int D, bool SAME_RHO>
+// MASKED: evaluate unconditionally and zero the kernel-gradient factor when r² > H² (every term
+// carries it), so that a caller can run several candidates back to back without branches.
+template <class T, int D, bool SAME_RHO, bool MASKED = false>
 SPH_HD void pair_fast(const Phys<T> &p, const FastTarget<T> &a, const T *xab, T r2, const T *va, const T *vb, T rho_b,
                       T P_b, T rhon_b, bool fluid_b, bool a_is_i, T &drho, T *acc) {
     // ∇W = fac * x_ab with fac = αD 5 (q−2)³ / (8h²), src/SPHKernels.jl:80-87.  q = clamp(d/h, 0, 2):
@@ -185,6 +187,7 @@ SPH_HD void pair_fast(const Phys<T> &p, const FastTarget<T> &a, const T *xab, T 
     T d = sph_sqrt_fast(r2);
     T qm2 = (sizeof(T) == 8) ? sph_min(d * p.h_inv, T(2)) - T(2) : d * p.h_inv - T(2);
     T fac = (p.gradw_c * qm2) * (qm2 * qm2);
+    if (MASKED) fac = (r2 <= p.H2) ? fac : T(0);
     T vdotx = T(0);
 #pragma unroll
     for (int k = 0; k < D; ++k) vdotx += (va[k] - vb[k]) * xab[k];

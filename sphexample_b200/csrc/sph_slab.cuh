@@ -6,7 +6,7 @@
 // [own_lo, own_hi) and holds a read-only copy of the neighbouring ranks' adjacent layer (the halo,
 // one cell = one interaction radius wide).  Traffic, all over NCCL send/recv on the handle's stream
 // (NVLink 5 / NVSwitch between the GPUs of a node):
-//   * every step:      one 4-word all-reduce (max) of the Δt / Δx reductions + error flag;
+//   * every step:      one 5-word all-reduce (max) of the Δt / Δx / |v| reductions + error flag;
 //   * every half step: the two boundary layers' packed state (A, B arrays) to the two neighbours
 //                      — plain contiguous ranges, no pack kernel, because sender and receiver hold
 //                      the layer in the same order (both sort stably, the receiver appends the

@@ -203,7 +203,7 @@ template <class T, int D>
 int Sim<T, D>::slab_allreduce_ctl() {
     k_slab_pre_allreduce<<<1, 1, 0, stream>>>(d_ctl.p);
     ++launches;
-    NCK(nccl::api().AllReduce(&d_ctl.p->red_disp2, &d_ctl.p->red_disp2, 4, nccl::Uint64, nccl::Max, slab.comm, stream));
+    NCK(nccl::api().AllReduce(&d_ctl.p->red_disp2, &d_ctl.p->red_disp2, 5, nccl::Uint64, nccl::Max, slab.comm, stream));
     return SPHB200_OK;
 }
 

@@ -22,18 +22,19 @@ __global__ void k_reduce_dt_dx(const typename Lay<T, D>::TA *__restrict__ A, con
                                int have_half, Ctl *ctl) {
     using L = Lay<T, D>;
     if (ctl->error || ctl->done) return;
-    T mdisp = T(0), mvisc = T(0), macc = T(0);
+    T mdisp = T(0), mvisc = T(0), macc = T(0), mvel = T(0);
     bool nan = false;
     for (int i = p0 + blockIdx.x * blockDim.x + threadIdx.x; i < p1; i += gridDim.x * blockDim.x) {
         T x[D], v[D], rs, P, a[D];
         L::unpack(A[i], B[i], x, v, rs, P);
         L::getv(acc[i], a);
-        T vx = T(0), xx = T(0), aa = T(0), dd = T(0);
+        T vx = T(0), xx = T(0), aa = T(0), dd = T(0), vv = T(0);
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             vx += v[k] * x[k];
             xx += x[k] * x[k];
             aa += a[k] * a[k];
+            vv += v[k] * v[k];
         }
         if (have_half) {
             T xh[D];
@@ -49,10 +50,12 @@ __global__ void k_reduce_dt_dx(const typename Lay<T, D>::TA *__restrict__ A, con
         mdisp = sph_max(mdisp, dd);
         mvisc = sph_max(mvisc, visc);
         macc = sph_max(macc, aa);
+        mvel = sph_max(mvel, vv);
     }
     mdisp = warp_max(mdisp);
     mvisc = warp_max(mvisc);
     macc = warp_max(macc);
+    mvel = warp_max(mvel);
     nan = __any_sync(0xffffffffu, nan);
     if ((threadIdx.x & 31) == 0) {
         if (nan) {
@@ -61,14 +64,21 @@ __global__ void k_reduce_dt_dx(const typename Lay<T, D>::TA *__restrict__ A, con
             if (mdisp > T(0)) atomic_max_nonneg(&ctl->red_disp2, (double)mdisp);
             if (mvisc > T(0)) atomic_max_nonneg(&ctl->red_visc, (double)mvisc);
             if (macc > T(0)) atomic_max_nonneg(&ctl->red_acc2, (double)macc);
+            if (mvel > T(0)) atomic_max_nonneg(&ctl->red_vel2, (double)mvel);
         }
     }
 }
 
 // One thread.  Finishes S0/S1, decides S2 (src/SPHCellList.jl:744-762) and the while-condition
 // (:742).  Arithmetic is carried out in T like the reference's (its scalars are ::T).
+// list_skin > 0 switches the per-particle neighbour lists on (sph_interact.cuh): a build pass
+// lists every candidate within H + skin; the lists stay exact while no two particles can have
+// approached by more than skin, i.e. while 2 x (bound on any particle's displacement since the
+// build) <= skin.  The bound: a full step moves a particle by dt (vₙ + vₙ₊₁)/2, at most
+// dt max(vmaxₙ, vmaxₙ₊₁); the half step of pass 2 by dt/2 · vₙ; moving bodies by their prescribed
+// speed (motion_vmax).
 template <class T>
-__global__ void k_step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl) {
+__global__ void k_step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, double list_skin, double motion_vmax) {
     if (ctl->red_err && !ctl->error) ctl->error = -(int)ctl->red_err;   // slab mode: another rank failed
     ctl->red_err = 0ull;
     if (ctl->error) return;
@@ -76,6 +86,8 @@ __global__ void k_step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl) {
     T disp = sph_sqrt((T)bits_to_double(ctl->red_disp2));
     T visc = (T)bits_to_double(ctl->red_visc);
     T acc2 = (T)bits_to_double(ctl->red_acc2);
+    const double vmax = fmax(sqrt(bits_to_double(ctl->red_vel2)), motion_vmax);
+    ctl->red_vel2 = 0ull;
     ctl->red_disp2 = 0ull;
     ctl->red_visc = 0ull;
     ctl->red_acc2 = 0ull;
@@ -107,7 +119,39 @@ __global__ void k_step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl) {
     ctl->red_acc2 = 0ull;
     ctl->work_counter[0] = 0;
     ctl->work_counter[1] = 0;
+    ctl->work_counter[2] = 0;
     ctl->step_open = 1;
+    // ---- which kernel serves the two passes of this step ---------------------------------------
+    ctl->list_mode[0] = ctl->list_mode[1] = 0;   // LM_CULL
+    ctl->list_build = 0;
+    if (list_skin > 0.0) {
+        if (ctl->list_fail) {          // the last build overflowed: no lists until the cells change
+            ctl->list_fail_last = ctl->list_fail;
+            ctl->list_fail = 0;
+            ctl->list_valid = 0;
+            ctl->list_off = 1;
+        }
+        if (ctl->do_rebuild) {
+            ctl->list_valid = 0;
+            ctl->list_off = 0;
+        }
+        const double margin = 0.49 * list_skin;
+        const double half = ctl->dt2 * vmax;
+        ctl->list_move += ctl->current_dt * fmax(ctl->list_prev_vmax, vmax);   // the step just completed
+        ctl->list_prev_vmax = vmax;
+        if (!ctl->list_off) {
+            if (ctl->list_valid && ctl->list_move + half <= margin) {
+                ctl->list_mode[0] = ctl->list_mode[1] = 2;          // LM_USE
+            } else {
+                ctl->list_build = 1;                                // k_list_build at xₙ, then both passes use it
+                ctl->list_mode[0] = 2;
+                ctl->list_mode[1] = (half <= margin) ? 2 : 0;
+                ctl->list_move = 0.0;
+                ctl->list_valid = 1;
+                ctl->n_list_builds += 1;
+            }
+        }
+    }
 }
 
 // UpdateMetaData!, src/SPHCellList.jl:679-685 (S19)
@@ -119,9 +163,17 @@ __global__ void k_step_end(Ctl *ctl) {
     ctl->step_open = 0;
 }
 
+// any change of positions or cells outside the step sequence voids the neighbour lists
+__global__ void k_invalidate_lists(Ctl *ctl) {
+    ctl->list_valid = 0;
+    ctl->list_build = 0;
+    ctl->list_mode[0] = ctl->list_mode[1] = 0;
+}
+
 __global__ void k_reset_counters(Ctl *ctl) {
     ctl->work_counter[0] = 0;
     ctl->work_counter[1] = 0;
+    ctl->work_counter[2] = 0;
 }
 
 // snapshot of ρₙ for the pass-2 diffusion / viscosity terms (Q2)

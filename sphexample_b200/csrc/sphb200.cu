@@ -54,6 +54,7 @@ struct sphb200_sim {
     virtual int download_aux(void *gradc, void *divr, void *ksum, void *kgrad) = 0;
     virtual int set_stream(void *stream) = 0;
     virtual int set_option(const char *name, double value) = 0;
+    virtual int get_stat(const char *name, double *value) = 0;
     virtual int comm_init(const uint8_t *id, int rank, int world, int axis) = 0;
     virtual int set_slab(int64_t lo, int64_t hi) = 0;
     virtual int column_histogram(int axis, int64_t *cell_min, int64_t *n_columns, int64_t *counts, int64_t cap) = 0;
@@ -183,6 +184,12 @@ class Sim final : public sphb200_sim {
     int64_t launches = 0;
     // options
     int opt_compact, opt_tma, opt_smem_kb, opt_batch;
+    int opt_lists, opt_lcap, opt_list_smem_kb;   // per-particle neighbour lists (sph_interact.cuh)
+    double opt_skin;                             // list skin as a fraction of H
+    DevBuf<uint4> nl;
+    DevBuf<int> nl_cnt;
+    size_t nl_stride = 0;
+    int cull_force = 1;   // the cull kernel ignores ctl->list_mode (lists off / stage-level calls)
     bool generic = false;
     AxisMap am;
     int ref_major_is_s = 1;
@@ -217,6 +224,12 @@ class Sim final : public sphb200_sim {
         opt_tma = env_int("SPHB200_TMA", 1);
         opt_smem_kb = env_int("SPHB200_SMEM_KB", sizeof(T) == 8 ? 40 : 24);
         opt_batch = env_int("SPHB200_BATCH", 64);
+        // lists: fp32 only by default (an fp64 3D window does not fit shared memory), never with
+        // PlanarShifting (the shifting displacement is not covered by the |v| dt bound)
+        opt_lists = env_int("SPHB200_LISTS", sizeof(T) == 4 ? 1 : 0);
+        opt_lcap = env_int("SPHB200_LCAP", D == 3 ? 320 : 96);
+        opt_list_smem_kb = env_int("SPHB200_LIST_SMEM_KB", 100);
+        opt_skin = env_int("SPHB200_SKIN_PCT", 10) * 0.01;
         am.ax_s = D - 1;   // default: the reference's most significant axis
         am.ax_m = (D == 3) ? 1 : 0;
         build_phys();
@@ -298,7 +311,27 @@ class Sim final : public sphb200_sim {
         else if (k == "smem_kb") opt_smem_kb = (int)value;
         else if (k == "batch") opt_batch = std::max(1, (int)value);
         else if (k == "generic") generic = generic || value != 0.0;
+        else if (k == "lists") opt_lists = (int)value;
+        else if (k == "skin") opt_skin = value;
+        else if (k == "lcap") opt_lcap = std::max(8, ((int)value + 7) & ~7);
+        else if (k == "list_smem_kb") opt_list_smem_kb = (int)value;
         else return fail(SPHB200_EINVAL, "unknown option '%s'", k.c_str());
+        return SPHB200_OK;
+    }
+
+    int get_stat(const char *name, double *value) override {
+        std::string k(name ? name : "");
+        if (!value) return fail(SPHB200_EINVAL, "get_stat: null output");
+        CK(cudaSetDevice(device));
+        int rc = sync_ctl();
+        if (rc) return rc;
+        if (k == "list_builds") *value = h_ctl->n_list_builds;
+        else if (k == "list_off") *value = h_ctl->list_off || h_ctl->list_fail;
+        else if (k == "list_fail_reason") *value = h_ctl->list_fail ? h_ctl->list_fail : h_ctl->list_fail_last;
+        else if (k == "halo_bytes_per_step") *value = (double)slab.halo_bytes_per_step;
+        else if (k == "migrated") *value = (double)slab.n_migrated;
+        else if (k == "n_total") *value = (double)n;
+        else return fail(SPHB200_EINVAL, "unknown stat '%s'", k.c_str());
         return SPHB200_OK;
     }
 
@@ -367,7 +400,7 @@ class Sim final : public sphb200_sim {
         CK(scan_partial.alloc((size_t)(cap / SCAN_CHUNK + 2)));
         cell_cap = cap;
         row_cap = cap / 3 + 1;
-        brick_cap = (int)std::min<long long>((long long)(n_alloc / BT) + row_cap + 16, INT_MAX);
+        brick_cap = (int)std::min<long long>((long long)(n_alloc / 8) + row_cap + 16, INT_MAX);
         CK(bricks.alloc((size_t)brick_cap));
         return SPHB200_OK;
     }
@@ -612,9 +645,139 @@ class Sim final : public sphb200_sim {
         k_gather_table<T, D><<<gp, 256, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, perm.p, table(false), table(true), key_tmp.p,
                                                      ccoord.p);
         k_copy_table<T, D><<<gp, 256, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, table(true), table(false));
-        k_build_bricks<<<1, 256, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, BT, bricks.p, brick_cap, count_rebuild);
-        k_finish_rebuild<<<1, 1, 0, stream>>>(d_ctl.p);
+        k_build_bricks<D><<<grid_for(row_cap, 128), 128, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, BT, brick_window_limit(),
+                                                                       bricks.p, brick_cap);
+        k_finish_rebuild<<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, count_rebuild);
         launches += 13;
+        CK(cudaGetLastError());
+        return SPHB200_OK;
+    }
+
+    bool lists_on() const { return opt_lists && !prm.shifting && opt_skin > 0.0; }
+    // candidates a brick's window may hold: what the list kernel can stage (pass 2 layout), else a
+    // bound that merely keeps sparse rows from producing row-long windows
+    int brick_window_limit() {
+        if (!lists_on()) return 8192;
+        int smem, cap;
+        if (generic ? list_geometry<1, true>(&smem, &cap) : list_geometry<1, false>(&smem, &cap)) return 8192;
+        return cap - 64;   // room for the 4-element alignment of the 3^(D-1) spans and the sentinel
+    }
+    double motion_vmax() const {
+        double v = 0.0;
+        for (int k = 0; k < motions.n; ++k) {
+            double d2 = 0.0;
+            for (int c = 0; c < D; ++c) d2 += motions.dir[k][c] * motions.dir[k][c];
+            v = std::max(v, fabs(motions.velocity[k]) * sqrt(d2));
+        }
+        return v;
+    }
+    int ensure_lists() {
+        if (!lists_on()) return SPHB200_OK;
+        const size_t need = (size_t)(opt_lcap / 8) * n_alloc;
+        if (nl.n < need || nl_stride != n_alloc) {
+            nl.release();
+            CK(nl.alloc(need));
+            CK(nl_cnt.alloc(n_alloc));
+            nl_stride = n_alloc;
+            k_invalidate_lists<<<1, 1, 0, stream>>>(d_ctl.p);
+            ++launches;
+        }
+        return SPHB200_OK;
+    }
+    void fill_args(InteractArgs<T, D> &g, int pass, int epilogue) {
+        memset(&g, 0, sizeof g);
+        g.A = pass ? Ah.p : A.p;
+        g.B = pass ? Bh.p : B.p;
+        g.RN = RN.p;
+        g.Bn = B2.p;   // vₙ snapshot (LaminarSPS pass 2, Q2); B itself is rewritten by the fused corrector
+        g.An_rw = A.p;
+        g.Bn_rw = B.p;
+        g.Ah_out = Ah.p;
+        g.Bh_out = Bh.p;
+        g.drhodt = drhodt.p;
+        g.acc = acc.p;
+        g.gradC = gradC.p;
+        g.divr = divr.p;
+        g.ksum = ksum.p;
+        g.kgrad = kgrad.p;
+        g.cell_start = cell_start.p;
+        g.ckey = ckey.p;
+        g.type = type.p;
+        g.bricks = bricks.p;
+        g.grid = d_grid.p;
+        g.ctl = d_ctl.p;
+        g.phys = ph;
+        g.epilogue = epilogue;
+        g.use_tma = opt_tma;
+        g.ref_major_is_s = ref_major_is_s;
+        g.counter_slot = pass;
+        g.nl = nl.p;
+        g.nl_cnt = nl_cnt.p;
+        g.nl_stride = nl_stride;
+        g.lcap = opt_lcap;
+        const double Hs = prm.H * (1.0 + opt_skin);
+        g.Hs2 = (T)(Hs * Hs);
+        g.force_cull = cull_force;
+    }
+    template <int PASS, bool GEN>
+    int list_geometry(int *smem_out, int *cap_out) {
+        using SS = StageSizes<T, D, PASS, GEN>;
+        int smem = std::min(opt_list_smem_kb, 220) * 1024;
+        int cap = std::min(((smem - 64) / SS::per_candidate) & ~3, LIST_IDX_MASK - 1);
+        *smem_out = cap * SS::per_candidate;
+        *cap_out = cap;
+        return cap >= 64 ? SPHB200_OK : fail(SPHB200_EINVAL, "list shared-memory budget too small");
+    }
+    template <int PASS, bool GEN>
+    int launch_list_t(int epilogue) {
+        auto kern = k_interact_list<T, D, PASS, GEN, BT>;
+        int smem, cap, rc;
+        if ((rc = list_geometry<PASS, GEN>(&smem, &cap))) return rc;
+        static int configured_smem = -1, ctas_per_sm = 0;
+        if (configured_smem != smem) {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, BT, smem));
+            configured_smem = smem;
+            if (ctas_per_sm < 1) return fail(SPHB200_ECUDA, "list kernel does not fit on an SM");
+        }
+        InteractArgs<T, D> g;
+        fill_args(g, PASS, epilogue);
+        g.list_cap_cand = cap;
+        int blocks = num_sms * ctas_per_sm;
+        int64_t maxb = (n + BT - 1) / BT + (int64_t)row_cap;
+        if ((int64_t)blocks > maxb) blocks = (int)std::max<int64_t>(1, maxb);
+        kern<<<blocks, BT, smem, stream>>>(g);
+        ++launches;
+        CK(cudaGetLastError());
+        return SPHB200_OK;
+    }
+
+    // the physics-free list build (runs only when k_step_control raised ctl->list_build)
+    template <bool GEN>
+    int launch_list_build() {
+        auto kern = k_list_build<T, D, GEN, BT>;
+        const int list_bytes = LIST_CAP * BT * 2;
+        int smem = std::min(opt_smem_kb, 200) * 1024;
+        int cap = std::min(((smem - 64) / (int)sizeof(TA)) & ~3, 32764);
+        smem = cap * (int)sizeof(TA) + list_bytes;
+        static int configured_smem = -1, ctas_per_sm = 0;
+        if (configured_smem != smem) {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, BT, smem));
+            configured_smem = smem;
+            if (ctas_per_sm < 1) return fail(SPHB200_ECUDA, "list-build kernel does not fit on an SM");
+        }
+        InteractArgs<T, D> g;
+        fill_args(g, 0, EPI_FUSED);
+        g.cap = cap;
+        int lsmem, lcap_cand, rc;
+        if ((rc = list_geometry<1, GEN>(&lsmem, &lcap_cand))) return rc;   // pass 2 stages ρₙ too: the tighter of the two
+        g.list_cap_cand = lcap_cand;
+        int blocks = num_sms * ctas_per_sm;
+        int64_t maxb = (n + BT - 1) / BT + (int64_t)row_cap;
+        if ((int64_t)blocks > maxb) blocks = (int)std::max<int64_t>(1, maxb);
+        kern<<<blocks, BT, smem, stream>>>(g);
+        ++launches;
         CK(cudaGetLastError());
         return SPHB200_OK;
     }
@@ -642,33 +805,8 @@ class Sim final : public sphb200_sim {
             if (ctas_per_sm < 1) return fail(SPHB200_ECUDA, "interaction kernel does not fit on an SM");
         }
         InteractArgs<T, D> g;
-        memset(&g, 0, sizeof g);
-        g.A = PASS ? Ah.p : A.p;
-        g.B = PASS ? Bh.p : B.p;
-        g.RN = RN.p;
-        g.Bn = B2.p;   // vₙ snapshot (LaminarSPS pass 2, Q2); B itself is rewritten by the fused corrector
-        g.An_rw = A.p;
-        g.Bn_rw = B.p;
-        g.Ah_out = Ah.p;
-        g.Bh_out = Bh.p;
-        g.drhodt = drhodt.p;
-        g.acc = acc.p;
-        g.gradC = gradC.p;
-        g.divr = divr.p;
-        g.ksum = ksum.p;
-        g.kgrad = kgrad.p;
-        g.cell_start = cell_start.p;
-        g.ckey = ckey.p;
-        g.type = type.p;
-        g.bricks = bricks.p;
-        g.grid = d_grid.p;
-        g.ctl = d_ctl.p;
-        g.phys = ph;
+        fill_args(g, PASS, epilogue);
         g.cap = cap;
-        g.epilogue = epilogue;
-        g.use_tma = opt_tma;
-        g.ref_major_is_s = ref_major_is_s;
-        g.counter_slot = PASS;
         int blocks = num_sms * ctas_per_sm;
         int64_t maxb = (n + BT - 1) / BT + (int64_t)row_cap;
         if ((int64_t)blocks > maxb) blocks = (int)std::max<int64_t>(1, maxb);
@@ -678,6 +816,20 @@ class Sim final : public sphb200_sim {
         return SPHB200_OK;
     }
     int launch_interact(int pass, int epilogue) {
+        if (lists_on() && epilogue == EPI_FUSED) {
+            // per pass two launches, exactly one of which does the work (ctl->list_mode[pass]): the
+            // cull kernel or the list kernel; pass 1 is preceded by the (predicated) list build
+            int rc = ensure_lists();
+            if (rc) return rc;
+            if (pass == 0 && (rc = generic ? launch_list_build<true>() : launch_list_build<false>())) return rc;
+            if ((rc = launch_cull(pass, epilogue, 0))) return rc;
+            if (generic) return pass ? launch_list_t<1, true>(epilogue) : launch_list_t<0, true>(epilogue);
+            return pass ? launch_list_t<1, false>(epilogue) : launch_list_t<0, false>(epilogue);
+        }
+        return launch_cull(pass, epilogue, 1);
+    }
+    int launch_cull(int pass, int epilogue, int force_cull) {
+        cull_force = force_cull;
         if (generic) return pass ? launch_interact_t<1, true, false>(epilogue) : launch_interact_t<0, true, false>(epilogue);
         if (opt_compact) return pass ? launch_interact_t<1, false, true>(epilogue) : launch_interact_t<0, false, true>(epilogue);
         return pass ? launch_interact_t<1, false, false>(epilogue) : launch_interact_t<0, false, false>(epilogue);
@@ -716,7 +868,8 @@ class Sim final : public sphb200_sim {
                                                                     d_ctl.p);
         int rc;
         if (slab.active && (rc = slab_allreduce_ctl())) return rc;
-        k_step_control<T><<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, ph.h, ph.c0, (T)prm.cfl);
+        k_step_control<T><<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, ph.h, ph.c0, (T)prm.cfl,
+                                               lists_on() ? opt_skin * prm.H : 0.0, motion_vmax());
         launches += 2;
         CK(cudaGetLastError());
         return SPHB200_OK;
@@ -772,7 +925,8 @@ class Sim final : public sphb200_sim {
                 if ((rc = enqueue_step_body())) return rc;
             }
             if ((rc = sync_ctl())) return rc;
-            while (h_ctl->error == SPHB200_ECAPACITY) {
+            for (int attempt = 0; h_ctl->error == SPHB200_ECAPACITY; ++attempt) {
+                if (attempt >= 3) return fail(SPHB200_ECAPACITY, "cell grid / brick list capacity exceeded");
                 if ((rc = recover_capacity())) return rc;
                 if (h_ctl->step_open && (rc = enqueue_step_body())) return rc;
                 if ((rc = sync_ctl())) return rc;
@@ -852,6 +1006,7 @@ class Sim final : public sphb200_sim {
         if (!uploaded) return fail(SPHB200_ESTATE, "update_neighbors before upload");
         CK(cudaSetDevice(device));
         if (slab.active) return fail(SPHB200_ESTATE, "stage-level calls are single-GPU only");
+        invalidate_lists();
         int rc;
         for (int attempt = 0; attempt < 3; ++attempt) {
             if ((rc = force_flag_rebuild())) return rc;
@@ -975,9 +1130,14 @@ class Sim final : public sphb200_sim {
         memcpy(&d, &b, 8);
         return d;
     }
+    void invalidate_lists() {
+        k_invalidate_lists<<<1, 1, 0, stream>>>(d_ctl.p);
+        ++launches;
+    }
     int progress_motion(double dt2) override {
         if (!uploaded) return fail(SPHB200_ESTATE, "progress_motion before upload");
         CK(cudaSetDevice(device));
+        invalidate_lists();
         return enqueue_motion(dt2);
     }
     int apply_mdbc() override {
@@ -991,6 +1151,7 @@ class Sim final : public sphb200_sim {
     int half_time_step(double dt2) override {
         if (!uploaded) return fail(SPHB200_ESTATE, "half_time_step before upload");
         CK(cudaSetDevice(device));
+        invalidate_lists();
         k_half_step<T, D><<<grid_for(n), 256, 0, stream>>>(A.p, B.p, acc.p, drhodt.p, type.p, Ah.p, Bh.p, 0, (int)n, ph, dt2, d_ctl.p);
         ++launches;
         CK(cudaGetLastError());
@@ -1000,6 +1161,7 @@ class Sim final : public sphb200_sim {
     int full_time_step(double dt) override {
         if (!have_half) return fail(SPHB200_ESTATE, "full_time_step before half_time_step");
         CK(cudaSetDevice(device));
+        invalidate_lists();
         k_full_step<T, D><<<grid_for(n), 256, 0, stream>>>(A.p, B.p, acc.p, drhodt.p, Ah.p, type.p, gradC.p, divr.p, 0, (int)n, ph,
                                                            dt, d_ctl.p);
         ++launches;
@@ -1194,6 +1356,7 @@ int sphb200_download_half(sphb200_sim *s, void *p, void *v, void *r, void *pr) {
 int sphb200_download_aux(sphb200_sim *s, void *g, void *d, void *k, void *kg) { NEED(s); return s->download_aux(g, d, k, kg); }
 int sphb200_set_stream(sphb200_sim *s, void *stream) { NEED(s); return s->set_stream(stream); }
 int sphb200_set_option(sphb200_sim *s, const char *name, double value) { NEED(s); return s->set_option(name, value); }
+int sphb200_get_stat(sphb200_sim *s, const char *name, double *value) { NEED(s); return s->get_stat(name, value); }
 int sphb200_stage_times(sphb200_sim *s, double *ms, int n) { NEED(s); return s->stage_times(ms, n); }
 int sphb200_comm_unique_id(uint8_t id_out[128]) { return slab_unique_id(id_out); }
 int sphb200_comm_init(sphb200_sim *s, const uint8_t id[128], int rank, int world, int axis) { NEED(s); return s->comm_init(id, rank, world, axis); }

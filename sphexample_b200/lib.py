@@ -81,6 +81,7 @@ def lib():
         "sphb200_launch_count": (i64, [sim]),
         "sphb200_set_stream": (C.c_int, [sim, vp]),
         "sphb200_set_option": (C.c_int, [sim, C.c_char_p, dbl]),
+        "sphb200_get_stat": (C.c_int, [sim, C.c_char_p, P(dbl)]),
         "sphb200_stage_times": (C.c_int, [sim, P(dbl), C.c_int]),
         "sphb200_update_neighbors": (C.c_int, [sim, P(i64)]),
         "sphb200_get_cell_list": (C.c_int, [sim, P(i64), vp, vp]),

@@ -144,6 +144,11 @@ class Simulation:
     def set_option(self, name: str, value: float):
         self._ck(self._L.sphb200_set_option(self._h, name.encode(), float(value)))
 
+    def stat(self, name: str) -> float:
+        v = C.c_double()
+        self._ck(self._L.sphb200_get_stat(self._h, name.encode(), C.byref(v)))
+        return float(v.value)
+
     def stage_times(self):
         ms = (C.c_double * 5)()
         self._ck(self._L.sphb200_stage_times(self._h, ms, 5))

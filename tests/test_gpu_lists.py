@@ -1,0 +1,102 @@
+"""Per-particle neighbour lists (csrc/sph_interact.cuh, k_interact_list): the list path must give
+the cull path's results — same accepted pair set (stale-cell window AND r² <= H² now), different
+summation order only — and must stay exact while particles move (skin bookkeeping), across
+rebuilds, and when a build overflows (fallback to the cull kernel)."""
+import numpy as np
+import pytest
+
+import util
+from sphexample_b200.simulation import Simulation
+
+pytestmark = pytest.mark.gpu
+
+
+def run(case, steps, **opts):
+    p = util.params_of(case)
+    sim = Simulation(p)
+    for k, v in opts.items():
+        sim.set_option(k, v)
+    sim.upload(case.particles)
+    rep = sim.step(steps, reset_delta_x=True)
+    st = sim.download(order="id")
+    stats = {"builds": sim.stat("list_builds"), "off": sim.stat("list_off")}
+    sim.close()
+    return rep, st, stats
+
+
+@pytest.mark.parametrize("name,steps,vel,tol", [
+    ("c1_2d_f64", 120, 0.5, 1e-11), ("c1_2d_f64", 200, 3.0, 1e-10),
+    ("c1_2d_f32", 120, 0.5, 2e-4), ("3d_f32", 80, 0.5, 2e-4), ("3d_f32", 150, 3.0, 1e-3),
+])
+def test_lists_match_cull_path(name, steps, vel, tol):
+    mk = {"c1_2d_f64": lambda: util.case_c1("float64"), "c1_2d_f32": lambda: util.case_c1("float32"),
+          "3d_f32": lambda: util.case_3d_small("float32")}[name]
+    r0, s0, st0 = run(util.perturb(mk(), vel_scale=vel), steps, lists=0)
+    r1, s1, st1 = run(util.perturb(mk(), vel_scale=vel), steps, lists=1)
+    assert st0["builds"] == 0 and st1["builds"] >= 1 and st1["off"] == 0
+    # far fewer builds than passes: the lists are actually reused
+    assert st1["builds"] < steps
+    assert r0["iteration"] == r1["iteration"] == steps and r0["n_rebuilds"] == r1["n_rebuilds"]
+    assert r1["total_time"] == pytest.approx(r0["total_time"], rel=1e-6 if "f32" in name else 1e-13)
+    for f in ("Position", "Velocity", "Density"):
+        util.check(util.relerr(s1[f], s0[f]), tol)
+
+
+def test_lists_match_oracle_fp64(oracle_lib):
+    case = util.perturb(util.case_c1("float64"), vel_scale=2.0)
+    p = util.params_of(case)
+    sim = Simulation(p)
+    sim.set_option("lists", 1)
+    sim.upload(case.particles)
+    o = oracle_lib.Oracle(p, case.particles, nthreads=4)
+    sim.step(150, reset_delta_x=True)
+    o.step(150, True)
+    st = sim.download(order="id")
+    assert sim.stat("list_builds") >= 2 and sim.stat("list_off") == 0
+    assert sim.report()["n_rebuilds"] == o.report()["n_rebuilds"]
+    util.check(util.relerr(st["Velocity"], util.by_id(o.ids, o.get("vel"))), 1e-9)
+    util.check(util.relerr(st["Density"], util.by_id(o.ids, o.get("rho"))), 1e-11)
+    sim.close()
+
+
+@pytest.mark.parametrize("skin", [0.02, 0.3])
+def test_skin_only_changes_the_build_cadence(skin):
+    mk = lambda: util.perturb(util.case_c1("float64"), vel_scale=2.0)
+    r0, s0, _ = run(mk(), 100, lists=0)
+    r1, s1, st1 = run(mk(), 100, lists=1, skin=skin)
+    assert st1["builds"] >= 1
+    for f in ("Position", "Velocity", "Density"):
+        util.check(util.relerr(s1[f], s0[f]), 1e-10)
+
+
+def test_overflowing_build_falls_back_to_the_cull_kernel():
+    mk = lambda: util.perturb(util.case_3d_small("float32"))
+    r0, s0, _ = run(mk(), 30, lists=0)
+    r1, s1, st1 = run(mk(), 30, lists=1, lcap=16)          # 16 entries cannot hold ~100 neighbours
+    assert st1["off"] == 1
+    r2, s2, st2 = run(mk(), 30, lists=1, list_smem_kb=8)   # window does not fit the list kernel's shared memory
+    assert st2["off"] == 1
+    for s in (s1, s2):
+        for f in ("Position", "Velocity", "Density"):
+            assert np.array_equal(s[f], s0[f]) or util.relerr(s[f], s0[f]) < 2e-4, f
+
+
+def test_stage_level_calls_void_the_lists(oracle_lib):
+    """positions changed outside the step sequence: the next step must rebuild its lists"""
+    case = util.perturb(util.case_c1("float64"))
+    p = util.params_of(case)
+    sim = Simulation(p)
+    sim.set_option("lists", 1)
+    sim.upload(case.particles)
+    o = oracle_lib.Oracle(p, case.particles, nthreads=4)
+    sim.step(5, reset_delta_x=True)
+    o.step(5, True)
+    b0 = sim.stat("list_builds")
+    sim.UpdateNeighbors()
+    o.update_neighbors()
+    sim.step(5)
+    o.step(5, False)
+    assert sim.stat("list_builds") > b0
+    st = sim.download(order="id")
+    util.check(util.relerr(st["Density"], util.by_id(o.ids, o.get("rho"))), 1e-11)
+    sim.close()
