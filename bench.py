@@ -139,16 +139,18 @@ def run_reference(args, rank, world):
             "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(n_full, args.gpus, note="reference arm: C++ restatement of the reference's "
-                                      "multi-threaded CPU algorithm (Julia unavailable), bounded sample"),
+                                      "multi-threaded CPU algorithm (Julia unavailable), bounded sample, from rest "
+                                      "(CPU cost per step does not depend on the flow state)", prep_time=args.prep_time),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_particles, gpus, note=None):
+def workload_config(n_particles, gpus, note=None, prep_time=0.0):
     cfg = {"workload": f"C3 3D dam-break lattice (example/Dambreak3d.jl constants, h=sqrt(3)dp, Wendland C2, "
-                       f"artificial viscosity + linear density diffusion), ~{PER_GPU_PARTICLES} particles per GPU",
+                       f"artificial viscosity + linear density diffusion), ~{PER_GPU_PARTICLES} particles per GPU, "
+                       f"state {prep_time:g} s after release (developed flow; 0 = at rest)",
            "particles": int(n_particles), "precision": "fp32 storage+compute",
            "parallelism": "single GPU" if gpus == 1 else f"y-slab decomposition over {gpus} GPUs, NCCL halo exchange",
            "l2_policy": "L2 flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs); "
@@ -158,6 +160,14 @@ def workload_config(n_particles, gpus, note=None):
     if note:
         cfg["note"] = note
     return cfg
+
+
+def max_over_ranks_host(torch, world, v):
+    if world == 1:
+        return v
+    t = torch.tensor([float(v)], device="cuda", dtype=torch.float64)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
 
 
 def run_ours(args, rank, world, local_rank):
@@ -185,11 +195,21 @@ def run_ours(args, rank, world, local_rank):
         mine = dec.mine
     else:
         mine = slice(None)
-    # pinned host copies of this rank's part of the caller's table (the reference-facing call takes host buffers)
-    host = {k: torch.from_numpy(np.ascontiguousarray(getattr(parts, k)[mine])).pin_memory().numpy()
-            for k in ("Position", "Velocity", "Density")}
-    types = np.ascontiguousarray(parts.Type[mine], np.uint8)
-    ids = np.ascontiguousarray(parts.ID[mine], np.int64)
+    # ---- workload state: the dam break t_prep seconds after release (developed flow) -------------
+    # generated by running the case itself from rest (untimed, part of building the synthetic input);
+    # the resulting per-rank particle table, in pinned HOST memory, is the benchmark's input
+    sim.upload_arrays(*(np.ascontiguousarray(getattr(parts, k)[mine]) for k in ("Position", "Velocity", "Density")),
+                      np.ascontiguousarray(parts.Type[mine], np.uint8), ids=np.ascontiguousarray(parts.ID[mine], np.int64))
+    prep = {"t_prep": args.prep_time, "steps": 0}
+    if args.prep_time > 0:
+        r = sim.SimulationLoop(args.prep_time)
+        prep["steps"] = int(r["iteration"])
+        sim.set_time(0.0, 0)
+    st0 = sim.download(fields=("Position", "Velocity", "Density", "Type", "ID"))
+    prep["vmax"] = float(max_over_ranks_host(torch, world, np.sqrt((st0["Velocity"].astype(np.float64) ** 2).sum(1)).max()))
+    host = {k: torch.from_numpy(np.ascontiguousarray(st0[k])).pin_memory().numpy() for k in ("Position", "Velocity", "Density")}
+    types = np.ascontiguousarray(st0["Type"], np.uint8)
+    ids = np.ascontiguousarray(st0["ID"], np.int64)
     n_local = int(types.shape[0])
 
     def upload():
@@ -229,6 +249,7 @@ def run_ours(args, rank, world, local_rank):
     # of the K per-step device times.  The un-flushed back-to-back figure is reported beside it.
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     l0 = sim.launch_count
+    rb0, lb0 = int(sim.report()["n_rebuilds"]), int(sim.stat("list_builds"))
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t0 = time.time()
@@ -242,7 +263,8 @@ def run_ours(args, rank, world, local_rank):
     t1 = time.time()
     ms = float(sum(a.elapsed_time(b) for a, b in ev))
     launches = sim.launch_count - l0
-    rebuilds_timed = int(rep["n_rebuilds"])
+    rebuilds_timed = int(rep["n_rebuilds"]) - rb0
+    list_builds_timed = int(sim.stat("list_builds")) - lb0
     # back-to-back (warm L2, one host sync per 64 steps on one GPU): what a production run sees
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -320,9 +342,10 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": workload_config(n, world), "clocks": clocks,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(n, world, prep_time=args.prep_time), "clocks": clocks,
                 "gpu_launches": int(launches), "roofline": roof, "e2e": e2e,
-                "rebuilds_in_timed_region": rebuilds_timed, "dp": dp,
+                "rebuilds_in_timed_region": rebuilds_timed, "list_builds_in_timed_region": list_builds_timed, "dp": dp,
+                "state": prep,
                 "back_to_back": {"value": n * args.steps / (ms_b2b * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_b2b / args.steps,
                                  "note": "same K steps enqueued back to back, warm L2"}}
         if world > 1:
@@ -367,6 +390,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=float, default=0, help="override the total particle count")
+    ap.add_argument("--prep-time", type=float, default=0.15,
+                    help="simulated seconds the dam break runs (untimed) before the benchmark state is taken; 0 = from rest")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
