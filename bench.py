@@ -294,12 +294,12 @@ def run_ours(args, rank, world, local_rank):
     achieved = 0.5 * (bytes_pass0 + bytes_pass1) / t_avg / 1e9
     prof = os.path.join(ROOT, "profiles", "interact_traffic.json")
     traffic = json.load(open(prof)).get("dram_bytes_per_launch") if os.path.exists(prof) else None
-    roof = {"bound": "hbm", "kernel": "k_interact<float,3,PASS,...> (avg of the two passes of a step, slowest rank)",
+    roof = {"bound": "hbm", "kernel": "k_interact_list<float,3,PASS> (+ k_list_build / k_interact when a pass cannot use the lists); avg of the two passes of a step, slowest rank",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "peak_source": how, "algorithmic_bytes_per_launch": 0.5 * (bytes_pass0 + bytes_pass1),
             "avg_launch_ms": 0.5 * (stage[2] + stage[3]),
-            "note": "compute-bound kernel (~18 kflop per particle per pass on the fp32 pipe, SURVEY 8d): "
-                    "the HBM fraction is reported because the metric asks for it",
+            "note": "not an HBM-bound kernel (~18 kflop per particle per pass, SURVEY 8d): bound by shared-memory gather "
+                    "bandwidth and fp32 issue slots (profiles/); the HBM fraction is reported because the metric asks for it",
             "stage_ms": {"reduce_control": stage[0], "rebuild_predicated": stage[1], "pass0_fused": stage[2],
                          "pass1_fused": stage[3], ("metadata" if world == 1 else "halo_exchanges"): stage[4]}}
 

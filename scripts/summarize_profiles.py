@@ -82,15 +82,21 @@ for rep in sorted(f for f in os.listdir(src) if f.endswith(".ncu-rep")):
     txt, js = full_capture(f"{src}/{rep}")
     open(P(f"{base}_ncu_full.txt"), "w").write(f"# ncu --set full --clock-control none --import-source on, {rep}\n" + txt)
     if "interact" in base and js:
+        # launches that did the work (the predicated twins of a pass return in microseconds)
+        def dur_us(d):
+            return d["gpu__time_duration.sum"] * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(d["gpu__time_duration.sum__unit"], 1.0)
+        busy = [d for d in js if dur_us(d) > 50.0 and "k_list_build" not in d["kernel"]]
         tr = [to_bytes(d["dram__bytes_read.sum"], d["dram__bytes_read.sum__unit"]) +
-              to_bytes(d["dram__bytes_write.sum"], d["dram__bytes_write.sum__unit"]) for d in js]
-        json.dump({"source": f"profiles/{tag}_{base}_ncu_full.txt", "kernels": [d["kernel"] for d in js],
-                   "dram_bytes_per_launch_each": tr, "dram_bytes_per_launch": sum(tr) / len(tr)},
-                  open("profiles/interact_traffic.json", "w"), indent=1)
+              to_bytes(d["dram__bytes_write.sum"], d["dram__bytes_write.sum__unit"]) for d in busy]
+        if tr:
+            json.dump({"source": f"profiles/{tag}_{base}_ncu_full.txt", "kernels": [d["kernel"] for d in busy],
+                       "duration_us": [dur_us(d) for d in busy],
+                       "dram_bytes_per_launch_each": tr, "dram_bytes_per_launch": sum(tr) / len(tr)},
+                      open("profiles/interact_traffic.json", "w"), indent=1)
     lines = subprocess.run([sys.executable, "scripts/ncu_lines.py", f"{src}/{rep}", "0", "0.8"], capture_output=True, text=True).stdout
     if lines.strip():
         open(P(f"{base}_source_lines.txt"), "w").write(lines)
-for name in ("bench.json", "sweep.jsonl", "host.txt", "smoke.log", "pytest_gpu.log", "bench_ref.json", "slab.jsonl"):
+for name in ("bench.json", "configs.jsonl", "sweep.jsonl", "host.txt", "smoke.log", "pytest_gpu.log", "bench_ref.json", "slab.jsonl"):
     if os.path.exists(f"{src}/{name}"):
         open(P(name), "w").write(open(f"{src}/{name}").read())
 if os.path.exists(f"{src}/parity.jsonl"):

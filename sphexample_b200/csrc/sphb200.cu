@@ -226,7 +226,8 @@ class Sim final : public sphb200_sim {
         opt_batch = env_int("SPHB200_BATCH", 64);
         // lists: fp32 only by default (an fp64 3D window does not fit shared memory), never with
         // PlanarShifting (the shifting displacement is not covered by the |v| dt bound)
-        opt_lists = env_int("SPHB200_LISTS", sizeof(T) == 4 ? 1 : 0);
+        // (2D fp64 windows fit too: C2 186 -> 325 Mpu/s, profiles/r1m_configs.jsonl)
+        opt_lists = env_int("SPHB200_LISTS", (sizeof(T) == 4 || D == 2) ? 1 : 0);
         opt_lcap = env_int("SPHB200_LCAP", D == 3 ? 320 : 96);
         opt_list_smem_kb = env_int("SPHB200_LIST_SMEM_KB", 72);   // 3 CTAs per SM (r1 sweep: 56 / 72 / 100 KB -> 0.81 / 0.69 / 0.80 ms per pass)
         opt_skin = env_int("SPHB200_SKIN_PCT", 10) * 0.01;
@@ -386,6 +387,10 @@ class Sim final : public sphb200_sim {
         if (prm.kernel_output) { CK(ksum.grow(na, keep, stream)); CK(kgrad.grow(na, keep, stream)); }
         CK(stage.grow(na * (size_t)(sizeof(T) * (4 * D + 2) + 8), 0, stream));
         n_alloc = na;
+        {
+            int rc = ensure_lists();
+            if (rc) return rc;
+        }
         brick_cap = 0;   // re-sized with the cell tables
         long long cc = cell_cap;
         cell_cap = 0;
@@ -414,6 +419,7 @@ class Sim final : public sphb200_sim {
         CK(cudaSetDevice(device));
         int rc = alloc_particles(count);
         if (rc) return rc;
+        if ((rc = ensure_lists())) return rc;
         n = count;
         // raw arrays -> staging -> packed layout on the device
         unsigned char *sp = stage.p;
