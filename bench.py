@@ -185,7 +185,8 @@ def run_ours(args, rank, world, local_rank):
     n = len(parts)
     p = params_of(case)
     sim = Simulation(p, device=local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()              # a real stream (the legacy default stream cannot be graph-captured)
+    torch.cuda.set_stream(stream)
     sim.set_stream(stream.cuda_stream)
     dec = None
     if world > 1:

@@ -30,8 +30,9 @@ def gpu_rate(case, steps, warm, **opts):
     sim.upload(case.particles)
     sim.step(warm, reset_delta_x=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real stream: the legacy default stream cannot be graph-captured
     sim.set_stream(stream.cuda_stream)
+    sim.step(2)                           # (captures the step graph; the oracle below takes these 2 steps too)
     torch.cuda.synchronize()
     e0.record(stream)
     sim.step(steps)
@@ -62,7 +63,7 @@ def row(name, case, steps, warm, cpu_steps, **opts):
     # parity after warm + steps steps (same cadence: one forced rebuild at the start)
     o = orc.Oracle(util.params_of(case), case.particles, nthreads=THREADS)
     o.step(warm, True)
-    o.step(steps, False)
+    o.step(steps + 2, False)
     ids = o.ids
     out = {"config": name, "n": len(case.particles), "float": case.meta.FloatType, "opts": opts, "steps": steps,
            "gpu_Mpu_s": round(rate, 2), "cpu_1thread_Mpu_s": round(r1, 4), "cpu_all_Mpu_s": round(rN, 4), "cpu_threads": THREADS,
@@ -74,10 +75,11 @@ def row(name, case, steps, warm, cpu_steps, **opts):
 
 
 row("C1 2D dam break shipped (6 881), fp64", util.case_c1("float64"), 400, 20, 40)
-row("C1 with lists", util.case_c1("float64"), 400, 20, 40, lists=1)
+row("C1 cull kernel only, no step graph", util.case_c1("float64"), 400, 20, 40, lists=0, graph=0)
 c2 = cases.case_dam_break_2d(0.0058, "float64")
 row("C2 2D dam break dp=0.0058 (59 909), fp64", c2, 400, 20, 10)
-row("C2 with lists", cases.case_dam_break_2d(0.0058, "float64"), 400, 20, 10, lists=1)
+row("C2 no step graph", cases.case_dam_break_2d(0.0058, "float64"), 400, 20, 10, graph=0)
+row("C2 cull kernel only, no step graph", cases.case_dam_break_2d(0.0058, "float64"), 400, 20, 10, lists=0, graph=0)
 row("C5 StillWedge mDBC (3 027), fp64", util.case_c5("float64"), 400, 20, 40)
 c3s = cases.case_dam_break_3d(0.0085, "float32")
 row("3D dam break at the shipped resolution dp=0.0085 (171 721), fp32", c3s, 200, 20, 5)

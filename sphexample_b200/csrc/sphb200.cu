@@ -224,6 +224,7 @@ class Sim final : public sphb200_sim {
         opt_tma = env_int("SPHB200_TMA", 1);
         opt_smem_kb = env_int("SPHB200_SMEM_KB", sizeof(T) == 8 ? 40 : 24);
         opt_batch = env_int("SPHB200_BATCH", 64);
+        opt_graph = env_int("SPHB200_GRAPH", 1);
         // lists: fp32 only by default (an fp64 3D window does not fit shared memory), never with
         // PlanarShifting (the shifting displacement is not covered by the |v| dt bound)
         // (2D fp64 windows fit too: C2 186 -> 325 Mpu/s, profiles/r1m_configs.jsonl)
@@ -236,6 +237,7 @@ class Sim final : public sphb200_sim {
         build_phys();
     }
     ~Sim() override {
+        drop_step_graph();
         if (slab.comm) nccl::api().CommDestroy(slab.comm);
         if (slab.d_counts) cudaFree(slab.d_counts);
         if (slab.h_counts) cudaFreeHost(slab.h_counts);
@@ -299,6 +301,7 @@ class Sim final : public sphb200_sim {
 
     int set_stream(void *s) override {
         CK(cudaSetDevice(device));
+        drop_step_graph();
         CK(cudaStreamSynchronize(stream));
         if (own_stream && stream) cudaStreamDestroy(stream);
         stream = (cudaStream_t)s;
@@ -307,6 +310,8 @@ class Sim final : public sphb200_sim {
     }
     int set_option(const char *name, double value) override {
         std::string k(name ? name : "");
+        drop_step_graph();
+        if (k == "graph") { opt_graph = (int)value; return SPHB200_OK; }
         if (k == "compact") opt_compact = (int)value;
         else if (k == "tma") opt_tma = (int)value;
         else if (k == "smem_kb") opt_smem_kb = (int)value;
@@ -345,6 +350,7 @@ class Sim final : public sphb200_sim {
     int alloc_particles(int64_t count) {
         size_t na = (size_t)((count + 3) & ~3ll) + 8;
         if (na <= n_alloc) return SPHB200_OK;
+        drop_step_graph();
         na = na + na / 8;   // headroom for slab migration
         CK(A.alloc(na)); CK(A2.alloc(na)); CK(Ah.alloc(na));
         CK(B.alloc(na)); CK(B2.alloc(na)); CK(Bh.alloc(na));
@@ -398,6 +404,7 @@ class Sim final : public sphb200_sim {
     }
     int alloc_cells(long long cells_needed) {
         long long cap = std::max<long long>(cells_needed, 4096);
+        if (cap > cell_cap) drop_step_graph();
         if (cap > (1ll << 28)) return fail(SPHB200_ECAPACITY, "cell grid of %lld cells exceeds the dense-grid limit", cap);
         if (cap <= cell_cap) return SPHB200_OK;
         CK(cell_count.alloc((size_t)cap + 8));
@@ -417,6 +424,7 @@ class Sim final : public sphb200_sim {
         if (count < 1 || count > (int64_t)INT_MAX / 8 || !pos || !rho || !ty)
             return fail(SPHB200_EINVAL, "upload: need n >= 1, position, density and type");
         CK(cudaSetDevice(device));
+        drop_step_graph();   // n is a kernel argument
         int rc = alloc_particles(count);
         if (rc) return rc;
         if ((rc = ensure_lists())) return rc;
@@ -909,6 +917,57 @@ class Sim final : public sphb200_sim {
         return push_ctl();
     }
 
+    // ---- one step = one CUDA graph launch ---------------------------------------------------------
+    // Every decision of a step lives on the device (Ctl) and every kernel is predicated on it, so the
+    // launch sequence of a step is static: it is captured once (≈ 25 kernels) and replayed.  That takes
+    // the host's per-launch cost and the inter-kernel gaps out of small cases (2D, 10^4-10^5 particles),
+    // where a step is shorter than its launch overhead.  Re-captured when anything a kernel argument
+    // depends on changes (upload, reallocation, options, stream).
+    cudaGraph_t step_graph = nullptr;
+    cudaGraphExec_t step_exec = nullptr;
+    int64_t step_graph_launches = 0;
+    int opt_graph = 1;
+    void drop_step_graph() {
+        if (step_exec) cudaGraphExecDestroy(step_exec);
+        if (step_graph) cudaGraphDestroy(step_graph);
+        step_exec = nullptr;
+        step_graph = nullptr;
+    }
+    int enqueue_step() {
+        int rc;
+        // (the legacy default stream cannot be captured: callers that hand it over via set_stream get plain launches)
+        if (!opt_graph || !have_half || !have_cells || stream == nullptr) {   // first steps: arguments still change, attributes get set
+            if ((rc = enqueue_step_head())) return rc;
+            return enqueue_step_body();
+        }
+        if (!step_exec) {
+            const int64_t l0 = launches;
+            if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                cudaGetLastError();
+                opt_graph = 0;   // not capturable here: plain launches from now on
+                if ((rc = enqueue_step_head())) return rc;
+                return enqueue_step_body();
+            }
+            rc = enqueue_step_head();
+            if (!rc) rc = enqueue_step_body();
+            cudaError_t e = cudaStreamEndCapture(stream, &step_graph);
+            if (rc) {
+                drop_step_graph();
+                return rc;
+            }
+            if (e != cudaSuccess) {
+                drop_step_graph();
+                return fail(SPHB200_ECUDA, "step graph capture failed: %s", cudaGetErrorString(e));
+            }
+            CK(cudaGraphInstantiate(&step_exec, step_graph, 0));
+            step_graph_launches = launches - l0;
+            launches = l0;
+        }
+        CK(cudaGraphLaunch(step_exec, stream));
+        launches += step_graph_launches;
+        return SPHB200_OK;
+    }
+
     int run_steps(int64_t nsteps, bool until_target) {
         if (!uploaded) return fail(SPHB200_ESTATE, "step before upload");
         CK(cudaSetDevice(device));
@@ -926,10 +985,8 @@ class Sim final : public sphb200_sim {
             } else {
                 batch = 1;
             }
-            for (int64_t s = 0; s < batch; ++s) {
-                if ((rc = enqueue_step_head())) return rc;
-                if ((rc = enqueue_step_body())) return rc;
-            }
+            for (int64_t s = 0; s < batch; ++s)
+                if ((rc = enqueue_step())) return rc;
             if ((rc = sync_ctl())) return rc;
             for (int attempt = 0; h_ctl->error == SPHB200_ECAPACITY; ++attempt) {
                 if (attempt >= 3) return fail(SPHB200_ECAPACITY, "cell grid / brick list capacity exceeded");
