@@ -291,12 +291,22 @@ int Sim<T, D>::slab_rebuild() {
 
 // S2 .. S19 of one step in slab mode (after the head has been synchronised); ev: optional 6 events
 // bracketing rebuild+motion+snapshots | pass 0 | halo n+1/2 | pass 1 | halo n+1
+// the step that raised do_rebuild paused itself (k_step_control): clear the pause, rebuild across
+// ranks; the caller then runs the body of the still-open step
 template <class T, int D>
-int Sim<T, D>::slab_step_body(cudaEvent_t *ev) {
+int Sim<T, D>::slab_resume_after_pause() {
+    h_ctl->done = 0;
+    int rc = push_ctl();
+    if (rc) return rc;
+    return slab_rebuild();
+}
+
+template <class T, int D>
+int Sim<T, D>::slab_step_body(cudaEvent_t *ev, bool host_synced) {
     int rc;
 #define EV(k) if (ev) CKS(cudaEventRecord(ev[k], stream))
     EV(0);
-    if (h_ctl->do_rebuild && (rc = slab_rebuild())) return rc;
+    if (host_synced && h_ctl->do_rebuild && (rc = slab_resume_after_pause())) return rc;
     if ((rc = enqueue_motion(-1.0))) return rc;                       // S3
     if ((rc = enqueue_snapshots())) return rc;
     EV(1);
@@ -325,7 +335,7 @@ int Sim<T, D>::slab_check_head(bool *stop, bool until_target) {
     if (h_ctl->error == SPHB200_ENUMERIC)
         return fail(SPHB200_ENUMERIC, "non-finite state or time step at iteration %lld (t = %g)", h_ctl->iteration, h_ctl->total_time);
     if (h_ctl->error) return fail(h_ctl->error, "device reported error %d (rank %d)", h_ctl->error, slab.rank);
-    *stop = until_target && h_ctl->done;
+    *stop = until_target && h_ctl->done && !h_ctl->do_rebuild;
     return SPHB200_OK;
 }
 
@@ -333,16 +343,37 @@ template <class T, int D>
 int Sim<T, D>::run_steps_slab(int64_t nsteps, bool until_target) {
     int rc = sync_ctl();
     if (rc) return rc;
+    const int64_t it0 = h_ctl->iteration;
     int64_t done_steps = 0;
+    const int64_t slab_batch = std::max(1, std::min(opt_batch, 16));
     while (until_target || done_steps < nsteps) {
-        bool stop = false;
-        if ((rc = slab_check_head(&stop, until_target))) return rc;
-        if (stop) break;
-        if ((rc = slab_step_body(nullptr))) return rc;
-        ++done_steps;
+        int64_t batch = slab_batch;
+        if (!until_target) batch = std::min<int64_t>(batch, nsteps - done_steps);
+        else if (h_ctl->current_dt > 0.0) {
+            double rem = (h_ctl->target_time - h_ctl->total_time) / h_ctl->current_dt;
+            batch = std::max<int64_t>(1, std::min<int64_t>(batch, (int64_t)(rem * 1.02) + 2));
+        } else {
+            batch = 1;
+        }
+        // enqueue a batch blind; a step that needs a rebuild pauses itself and everything behind it
+        for (int64_t k = 0; k < batch; ++k) {
+            if ((rc = enqueue_step_head())) return rc;
+            if ((rc = slab_step_body(nullptr, false))) return rc;
+        }
+        if ((rc = sync_ctl())) return rc;
+        if (h_ctl->error == SPHB200_ENUMERIC)
+            return fail(SPHB200_ENUMERIC, "non-finite state or time step at iteration %lld (t = %g)", h_ctl->iteration, h_ctl->total_time);
+        if (h_ctl->error) return fail(h_ctl->error, "device reported error %d (rank %d)", h_ctl->error, slab.rank);
+        if (h_ctl->done && h_ctl->do_rebuild) {
+            // paused at a rebuild: every rank sees the same flags (identical all-reduced inputs)
+            if ((rc = slab_resume_after_pause())) return rc;
+            if ((rc = slab_step_body(nullptr, false))) return rc;     // the open step
+            if ((rc = sync_ctl())) return rc;
+            if (h_ctl->error) return fail(h_ctl->error, "device reported error %d (rank %d)", h_ctl->error, slab.rank);
+        }
+        done_steps = h_ctl->iteration - it0;
+        if (until_target && h_ctl->done && !h_ctl->do_rebuild) break;
     }
-    if ((rc = sync_ctl())) return rc;
-    if (h_ctl->error) return fail(h_ctl->error, "device reported error %d (rank %d)", h_ctl->error, slab.rank);
     return SPHB200_OK;
 }
 

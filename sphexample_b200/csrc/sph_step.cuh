@@ -77,8 +77,13 @@ __global__ void k_reduce_dt_dx(const typename Lay<T, D>::TA *__restrict__ A, con
 // build) <= skin.  The bound: a full step moves a particle by dt (vₙ + vₙ₊₁)/2, at most
 // dt max(vmaxₙ, vmaxₙ₊₁); the half step of pass 2 by dt/2 · vₙ; moving bodies by their prescribed
 // speed (motion_vmax).
+// pause_on_rebuild (slab mode): a rebuild needs the host (exchange sizes), so the step that raises
+// do_rebuild also raises `done`: this step's body and every later enqueued step run empty until the
+// host has rebuilt and resumes the open step — steps can be enqueued in batches without a per-step
+// host round trip and without ever running a step on stale cells.
 template <class T>
-__global__ void k_step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, double list_skin, double motion_vmax) {
+__global__ void k_step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, double list_skin, double motion_vmax,
+                               int pause_on_rebuild) {
     if (ctl->red_err && !ctl->error) ctl->error = -(int)ctl->red_err;   // slab mode: another rank failed
     ctl->red_err = 0ull;
     if (ctl->error) return;
@@ -152,6 +157,7 @@ __global__ void k_step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, doubl
             }
         }
     }
+    if (pause_on_rebuild && ctl->do_rebuild) ctl->done = 1;
 }
 
 // UpdateMetaData!, src/SPHCellList.jl:679-685 (S19)

@@ -883,7 +883,7 @@ class Sim final : public sphb200_sim {
         int rc;
         if (slab.active && (rc = slab_allreduce_ctl())) return rc;
         k_step_control<T><<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, ph.h, ph.c0, (T)prm.cfl,
-                                               lists_on() ? opt_skin * prm.H : 0.0, motion_vmax());
+                                               lists_on() ? opt_skin * prm.H : 0.0, motion_vmax(), slab.active ? 1 : 0);
         launches += 2;
         CK(cudaGetLastError());
         return SPHB200_OK;
@@ -1009,7 +1009,8 @@ class Sim final : public sphb200_sim {
     int slab_allreduce_ctl();
     int slab_sort(const SlabFilter &flt, int count_rebuild);
     int slab_rebuild();
-    int slab_step_body(cudaEvent_t *ev);
+    int slab_step_body(cudaEvent_t *ev, bool host_synced = true);
+    int slab_resume_after_pause();
     int slab_check_head(bool *stop, bool until_target);
     int slab_stage_times(double *ms_out, int cnt);
 
