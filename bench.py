@@ -189,7 +189,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_stream(stream)
     sim.set_stream(stream.cuda_stream)
     dec = None
-    if world > 1:
+    if world > 1 or os.environ.get("SPHB200_BENCH_FORCE_SLAB"):   # (world of one: the slab code path without neighbours)
         from sphexample_b200 import slab
         dec = slab.SlabDecomposition(sim, parts, p.H_inv, rank, world, axis=SLAB_AXIS)
         dec.join()

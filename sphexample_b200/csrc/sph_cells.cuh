@@ -127,6 +127,7 @@ __global__ void k_grid_setup(Ctl *ctl, GridInfo *grid, AxisMap am, long long cel
     grid->ncell = (int)ncell;
     grid->nrows = (int)nrows;
     grid->nbricks = 0;   // k_build_bricks appends
+    grid->nbricks_bnd = 0;
     // owned rows: slab coordinate c_s in [own_lo, own_hi)
     long long s0 = (long long)own_lo - grid->cmin[am.ax_s];
     long long s1 = (long long)own_hi - grid->cmin[am.ax_s];
@@ -370,14 +371,22 @@ __global__ void k_copy_table(const Ctl *ctl, const GridInfo *grid, const int *__
 // keeps sparse rows (two tank walls 100 cells apart in one row) from producing bricks whose
 // window spans the whole row.  One thread per row, two passes (count, write); bricks are appended
 // through an atomic counter, so their order (not their content) varies from run to run.
+// `part` selects the rows: 0 = all owned rows; 1 = the first and last owned slab layer (their
+// particles are what the neighbour ranks hold as halo, so these bricks are computed first and their
+// results travel while the interior is computed); 2 = the layers in between.
 template <int D>
 __global__ void k_build_bricks(Ctl *ctl, GridInfo *grid, const int *__restrict__ cell_start, int bt, int wlimit,
-                               Brick *__restrict__ bricks, int brick_cap) {
+                               Brick *__restrict__ bricks, int brick_cap, int part) {
     if (ctl->error || ctl->done || !ctl->do_rebuild) return;
     constexpr int NR = (D == 3) ? 9 : 3;
     const int nx = grid->nx, nm = grid->nm;
-    const int r0 = grid->own_row0, r1 = grid->own_row1;
+    const int o0 = grid->own_row0, o1 = grid->own_row1;
+    const int i0 = min(o0 + nm, o1), i1 = max(o1 - nm, i0);     // interior rows [i0, i1)
+    int r0 = o0, r1 = o1, skip0 = 0, skip1 = 0;                 // rows [r0, r1) minus [skip0, skip1)
+    if (part == 1) { skip0 = i0; skip1 = i1; }
+    if (part == 2) { r0 = i0; r1 = i1; }
     for (int r = r0 + blockIdx.x * blockDim.x + threadIdx.x; r < r1; r += gridDim.x * blockDim.x) {
+        if (r >= skip0 && r < skip1) continue;
         const int rowbase = r * nx;
         const int p0 = cell_start[rowbase], p1 = cell_start[rowbase + nx];
         if (p1 <= p0) continue;
@@ -438,6 +447,11 @@ __global__ void k_build_bricks(Ctl *ctl, GridInfo *grid, const int *__restrict__
             }
         }
     }
+}
+
+__global__ void k_mark_boundary_bricks(const Ctl *ctl, GridInfo *grid) {
+    if (ctl->error || ctl->done || !ctl->do_rebuild) return;
+    grid->nbricks_bnd = grid->nbricks;
 }
 
 // last kernel of the rebuild sequence: table layout for the slab exchange, and a successful

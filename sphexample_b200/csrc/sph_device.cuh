@@ -90,7 +90,8 @@ struct Ctl {
     unsigned long long red_err;   // slab mode: max over ranks of -error (all-reduced with the three above)
     unsigned long long red_vel2;  // max |v|² (bounds the displacement the neighbour lists have to absorb)
     // work distribution of the interaction kernel
-    int work_counter[3];       // [0], [1]: the two passes; [2]: the list build
+    int bnd_done[2];           // slab mode: boundary-layer bricks finished in pass 1 / pass 2 of this step
+    int work_counter[8];       // [pass * 3 + part] (part 0 all / 1 boundary / 2 interior bricks); [6]: the list build
     // per-particle neighbour lists (sph_interact.cuh): which kernel serves each pass of this step
     int list_mode[2];          // LM_CULL / LM_USE
     int list_build;            // this step starts with a list build (k_list_build)
@@ -108,6 +109,7 @@ struct GridInfo {
     int cmin[3];               // cell coordinate of grid index 0 per axis (= bb_min - 1)
     int nx, nm, ns;            // dense grid extents: x fastest, then m, then s (slab axis)
     int ncell, nrows, nbricks;
+    int nbricks_bnd;           // bricks [0, nbricks_bnd) lie in the first / last owned slab layer (slab mode)
     int own_row0, own_row1;    // rows [own_row0, own_row1) are owned by this rank (slab mode)
     int own_p0, own_p1;        // owned particle index range in sorted order
     int own_l1, own_l2;        // [own_p0, own_l1) = first owned slab layer, [own_l2, own_p1) = last one

@@ -65,6 +65,12 @@ struct InteractArgs {
     int use_tma;                       // 1: cp.async.bulk staging, 0: cooperative ld/st staging
     int ref_major_is_s;                // 1: slab axis is the reference's most significant axis
     int counter_slot;                  // which ctl->work_counter this launch consumes
+    int brick_part;                    // 0: all bricks, 1: slab-boundary bricks, 2: interior bricks
+    // slab mode, single launch per pass: the boundary-layer bricks [0, nbricks_bnd) are taken first;
+    // the CTA that finishes the last of them raises *bnd_flag to bnd_epoch, which releases the halo
+    // exchange waiting on another stream (cuStreamWaitValue32) while the interior bricks go on
+    unsigned *bnd_flag;
+    unsigned bnd_epoch;
     // per-particle neighbour lists (sph_interact.cuh, "lists"): entry k of particle i is the u16
     // ((k & 7)-th half-word of) nl[(k >> 3) * nl_stride + i]
     uint4 *nl;
@@ -89,6 +95,19 @@ struct StageSizes {
     static constexpr int esBn = (PASS && GENERIC) ? sizeof(typename L::TB) : 0;
     static constexpr int per_candidate = esA + esB + esR + esBn;
 };
+
+// Called by every thread after the end-of-brick barrier (all of the brick's results are written).
+template <class T, int D>
+__device__ __forceinline__ void signal_boundary_brick(const InteractArgs<T, D> &g, int bidx, int pass) {
+    if (g.bnd_flag == nullptr || threadIdx.x != 0) return;
+    const int nbnd = g.grid->nbricks_bnd;
+    if (bidx >= nbnd) return;
+    __threadfence();
+    if (atomicAdd(&g.ctl->bnd_done[pass], 1) + 1 == nbnd) {
+        __threadfence_system();
+        atomicMax(g.bnd_flag, g.bnd_epoch);
+    }
+}
 
 // Per-particle tail of a pass: plain stores (stage-level entry points) or the fused symplectic
 // half / full update, shared by the cull kernel and the list kernel.
@@ -189,13 +208,15 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
 
     const int nx = g.grid->nx, nm = g.grid->nm;
     const int nbricks = g.grid->nbricks;
+    const int brick_first = g.brick_part == 2 ? g.grid->nbricks_bnd : 0;
+    const int brick_end = g.brick_part == 1 ? g.grid->nbricks_bnd : nbricks;
     const int npad = (g.grid->n_total + 3) & ~3;
 
     for (;;) {
-        if (tid == 0) s_brick = atomicAdd(&g.ctl->work_counter[g.counter_slot], 1);
+        if (tid == 0) s_brick = brick_first + atomicAdd(&g.ctl->work_counter[g.counter_slot], 1);
         __syncthreads();
         const int bidx = s_brick;
-        if (bidx >= nbricks) break;
+        if (bidx >= brick_end) break;
         const Brick br = g.bricks[bidx];
         const int key0 = g.ckey[br.t0], key1 = g.ckey[br.t1 - 1];
         const int cx0 = key0 % nx, cx1 = key1 % nx;
@@ -463,6 +484,7 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
         // ---- epilogue ---------------------------------------------------------------------
         if (valid) interact_epilogue<T, D, PASS, GENERIC>(g, i, xa, va, rho_a, sacc, drho, acc);
         __syncthreads();   // s_brick / s_off reuse
+        signal_boundary_brick(g, bidx, PASS);
     }
 }
 
@@ -508,7 +530,7 @@ __global__ void __launch_bounds__(BT) k_list_build(const InteractArgs<T, D> g) {
     const T Hs2 = g.Hs2;
 
     for (;;) {
-        if (tid == 0) s_brick = atomicAdd(&g.ctl->work_counter[2], 1);
+        if (tid == 0) s_brick = atomicAdd(&g.ctl->work_counter[6], 1);
         __syncthreads();
         const int bidx = s_brick;
         if (bidx >= nbricks) break;
@@ -724,13 +746,15 @@ __global__ void __launch_bounds__(BT) k_interact_list(const InteractArgs<T, D> g
 
     const int nx = g.grid->nx, nm = g.grid->nm;
     const int nbricks = g.grid->nbricks;
+    const int brick_first = g.brick_part == 2 ? g.grid->nbricks_bnd : 0;
+    const int brick_end = g.brick_part == 1 ? g.grid->nbricks_bnd : nbricks;
     const int npad = (g.grid->n_total + 3) & ~3;
 
     for (;;) {
-        if (tid == 0) s_brick = atomicAdd(&g.ctl->work_counter[g.counter_slot], 1);
+        if (tid == 0) s_brick = brick_first + atomicAdd(&g.ctl->work_counter[g.counter_slot], 1);
         __syncthreads();
         const int bidx = s_brick;
-        if (bidx >= nbricks) break;
+        if (bidx >= brick_end) break;
         const Brick br = g.bricks[bidx];
         const int key0 = g.ckey[br.t0], key1 = g.ckey[br.t1 - 1];
         const int cx0 = key0 % nx, cx1 = key1 % nx;
@@ -918,6 +942,7 @@ __global__ void __launch_bounds__(BT) k_interact_list(const InteractArgs<T, D> g
         }
         if (valid) interact_epilogue<T, D, PASS, GENERIC>(g, i, xa, va, rho_a, sacc, drho, acc);
         __syncthreads();   // shared window / s_brick reuse
+        signal_boundary_brick(g, bidx, PASS);
     }
 }
 

@@ -9,8 +9,11 @@
 //   * every step:      one 5-word all-reduce (max) of the Δt / Δx / |v| reductions + error flag;
 //   * every half step: the two boundary layers' packed state (A, B arrays) to the two neighbours
 //                      — plain contiguous ranges, no pack kernel, because sender and receiver hold
-//                      the layer in the same order (both sort stably, the receiver appends the
-//                      block in the sender's order);
+//                      the layer in the same order (both sort by the same order keys).  A pass is
+//                      ONE launch that takes the bricks of the two boundary layers first; the CTA
+//                      that retires the last of them raises a flag in device memory, on which the
+//                      exchange stream waits (cuStreamWaitValue32) — so the exchange runs while the
+//                      same launch computes the interior bricks;
 //   * every rebuild:   migration of the particles that left the slab, then the boundary layers'
 //                      full records.
 // NCCL is dlopen()ed (the copy already loaded in the process, e.g. torch's, else libnccl.so.2) so
@@ -92,6 +95,14 @@ struct SlabComm {
     int rank = 0, world = 1;
     int left = -1, right = -1;      // neighbour ranks along the slab axis (-1: domain end)
     nccl::comm_t comm = nullptr;
+    cudaStream_t xstream = nullptr; // the half-step halo exchanges run here, beside the interior bricks
+    cudaEvent_t ev_bnd = nullptr, ev_x = nullptr;
+    cudaEvent_t *dbg_ev = nullptr;  // timing probes of one step (slab_stage_times with SPHB200_SLAB_DEBUG)
+    // single-launch passes: the kernel raises *d_flag to `epoch` when its boundary bricks are done,
+    // the exchange stream waits for that value (driver API cuStreamWaitValue32)
+    unsigned *d_flag = nullptr;
+    unsigned epoch = 0;
+    int (*wait_value32)(cudaStream_t, unsigned long long, unsigned, unsigned) = nullptr;
     int *d_counts = nullptr;        // 8 ints on the device: migration / halo count exchange
     int *h_counts = nullptr;        // pinned mirror
     // host mirrors of the table layout after the last rebuild (sorted order):
@@ -141,6 +152,10 @@ __global__ void k_slab_check_arrivals(const typename Lay<T, D>::TA *__restrict__
         if (c < own_lo || c >= own_hi) atomicCAS(&ctl->error, 0, SPH_ERR_ESTATE);
     }
 }
+
+// end of a pass: raise the flag unconditionally — it is already up unless the pass ran empty
+// (error / pause), in which case the exchange stream must not be left waiting
+__global__ void k_slab_signal(unsigned *flag, unsigned epoch) { atomicMax(flag, epoch); }
 
 __global__ void k_slab_pre_allreduce(Ctl *ctl) {
     ctl->red_err = ctl->error ? (unsigned long long)(-ctl->error) : 0ull;

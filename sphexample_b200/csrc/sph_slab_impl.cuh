@@ -65,6 +65,23 @@ int Sim<T, D>::comm_init(const uint8_t *uid, int rank, int world, int axis) {
     slab.world = world;
     slab.left = rank > 0 ? rank - 1 : -1;
     slab.right = rank + 1 < world ? rank + 1 : -1;
+    {
+        int prio_lo = 0, prio_hi = 0;
+        CKS(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CKS(cudaStreamCreateWithPriority(&slab.xstream, cudaStreamNonBlocking, prio_hi));
+    }
+    CKS(cudaEventCreateWithFlags(&slab.ev_bnd, cudaEventDisableTiming));
+    CKS(cudaEventCreateWithFlags(&slab.ev_x, cudaEventDisableTiming));
+    CKS(cudaMalloc((void **)&slab.d_flag, sizeof(unsigned)));
+    CKS(cudaMemset(slab.d_flag, 0, sizeof(unsigned)));
+    {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (!getenv("SPHB200_SLAB_SPLIT") &&
+            cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            *(void **)(&slab.wait_value32) = fn;
+        cudaGetLastError();
+    }
     CKS(cudaMalloc((void **)&slab.d_counts, 8 * sizeof(int)));
     CKS(cudaMallocHost((void **)&slab.h_counts, 8 * sizeof(int)));
     am.ax_s = axis;
@@ -171,7 +188,7 @@ int Sim<T, D>::slab_exchange_records(Table<T, D> from, int sl0, int nl, int sr0,
 
 // the half-step exchange: boundary layers of two packed arrays to the neighbours' halo ranges
 template <class T, int D>
-int Sim<T, D>::slab_exchange_halo(TA *a, TB *b) {
+int Sim<T, D>::slab_exchange_halo(TA *a, TB *b, cudaStream_t stream) {
     const SlabComm &s = slab;
     const int nf = s.l1 - s.own_p0, nl = s.own_p1 - s.l2, hl = s.own_p0, hr = (int)n - s.own_p1;
     NCK(nccl::api().GroupStart());
@@ -291,6 +308,58 @@ int Sim<T, D>::slab_rebuild() {
 
 // S2 .. S19 of one step in slab mode (after the head has been synchronised); ev: optional 6 events
 // bracketing rebuild+motion+snapshots | pass 0 | halo n+1/2 | pass 1 | halo n+1
+// One interaction pass over the owned bricks with its halo exchange hidden behind the interior
+// bricks.  Nothing the exchange writes (the halo ranges of xa/xb) is read, and nothing it reads is
+// written, before the next pass.
+template <class T, int D>
+int Sim<T, D>::slab_pass(int pass, TA *xa, TB *xb) {
+    int rc;
+    cudaEvent_t *dbg = slab.dbg_ev ? slab.dbg_ev + pass * 5 : nullptr;   // optional timing probes (SPHB200_SLAB_DEBUG)
+    if (dbg) CKS(cudaEventRecord(dbg[0], stream));
+    if (slab.wait_value32) {
+        // one launch: boundary bricks first, the flag releases the exchange, interior bricks go on
+        const unsigned epoch = ++slab.epoch;
+        if (slab.wait_value32(slab.xstream, (unsigned long long)(uintptr_t)slab.d_flag, epoch, 0u /* GEQ */) != 0)
+            return fail(SPHB200_ECUDA, "cuStreamWaitValue32 failed");
+        if (dbg) CKS(cudaEventRecord(dbg[2], slab.xstream));
+        if ((rc = slab_exchange_halo(xa, xb, slab.xstream))) return rc;
+        CKS(cudaEventRecord(slab.ev_x, slab.xstream));
+        if (dbg) CKS(cudaEventRecord(dbg[3], slab.xstream));
+        bnd_flag = slab.d_flag;
+        bnd_epoch = epoch;
+        rc = launch_interact(pass, EPI_FUSED);
+        bnd_flag = nullptr;
+        if (rc) return rc;
+        k_slab_signal<<<1, 1, 0, stream>>>(slab.d_flag, epoch);
+        ++launches;
+        if (dbg) CKS(cudaEventRecord(dbg[4], stream));
+        if (dbg) CKS(cudaEventRecord(dbg[1], stream));
+        CKS(cudaStreamWaitEvent(stream, slab.ev_x, 0));
+        return SPHB200_OK;
+    }
+    // fallback (no stream memory operations): two launches, boundary bricks then interior bricks
+    brick_part = 1;
+    rc = launch_interact(pass, EPI_FUSED);
+    if (!rc) {
+        CKS(cudaEventRecord(slab.ev_bnd, stream));
+        if (dbg) CKS(cudaEventRecord(dbg[1], stream));
+        CKS(cudaStreamWaitEvent(slab.xstream, slab.ev_bnd, 0));
+        if (dbg) CKS(cudaEventRecord(dbg[2], slab.xstream));
+        rc = slab_exchange_halo(xa, xb, slab.xstream);
+    }
+    if (!rc) {
+        CKS(cudaEventRecord(slab.ev_x, slab.xstream));
+        if (dbg) CKS(cudaEventRecord(dbg[3], slab.xstream));
+        brick_part = 2;
+        rc = launch_interact(pass, EPI_FUSED);
+        if (dbg) CKS(cudaEventRecord(dbg[4], stream));
+    }
+    brick_part = 0;
+    if (rc) return rc;
+    CKS(cudaStreamWaitEvent(stream, slab.ev_x, 0));
+    return SPHB200_OK;
+}
+
 // the step that raised do_rebuild paused itself (k_step_control): clear the pause, rebuild across
 // ranks; the caller then runs the body of the still-open step
 template <class T, int D>
@@ -310,16 +379,14 @@ int Sim<T, D>::slab_step_body(cudaEvent_t *ev, bool host_synced) {
     if ((rc = enqueue_motion(-1.0))) return rc;                       // S3
     if ((rc = enqueue_snapshots())) return rc;
     EV(1);
-    if ((rc = launch_interact(0, EPI_FUSED))) return rc;              // S4-S10, S13 (owned bricks)
+    if ((rc = slab_pass(0, Ah.p, Bh.p))) return rc;                   // S4-S10, S13 + halo state n+1/2
     if ((rc = enqueue_motion(-1.0))) return rc;                       // S12
     EV(2);
-    if ((rc = slab_exchange_halo(Ah.p, Bh.p))) return rc;             // state n+1/2 of the halo layers
     EV(3);
-    if ((rc = launch_interact(1, EPI_FUSED))) return rc;              // S11, S14-S18
+    if ((rc = slab_pass(1, A.p, B.p))) return rc;                     // S11, S14-S18 + halo state n+1
     k_step_end<<<1, 1, 0, stream>>>(d_ctl.p);                         // S19
     ++launches;
     EV(4);
-    if ((rc = slab_exchange_halo(A.p, B.p))) return rc;               // state n+1 of the halo layers
     EV(5);
 #undef EV
     have_half = true;
@@ -378,7 +445,8 @@ int Sim<T, D>::run_steps_slab(int64_t nsteps, bool until_target) {
 }
 
 // slab-mode stage times of ONE extra step (collective): [0] reductions + all-reduce + control,
-// [1] rebuild + motion + snapshots, [2] pass 0, [3] pass 1, [4] the two halo exchanges
+// [1] rebuild + motion + snapshots, [2] pass 0, [3] pass 1 (each incl. whatever of its halo exchange
+// the interior bricks did not hide), [4] 0
 template <class T, int D>
 int Sim<T, D>::slab_stage_times(double *ms_out, int cnt) {
     cudaEvent_t ev[7];
@@ -387,8 +455,29 @@ int Sim<T, D>::slab_stage_times(double *ms_out, int cnt) {
     bool stop = false;
     int rc = slab_check_head(&stop, false);
     if (rc) return rc;
-    if ((rc = slab_step_body(ev))) return rc;
+    cudaEvent_t dbg[10];
+    const bool debug = getenv("SPHB200_SLAB_DEBUG") != nullptr;
+    if (debug) {
+        for (auto &e : dbg) CKS(cudaEventCreate(&e));
+        slab.dbg_ev = dbg;
+    }
+    rc = slab_step_body(ev);
+    slab.dbg_ev = nullptr;
+    if (rc) return rc;
     CKS(cudaStreamSynchronize(stream));
+    CKS(cudaStreamSynchronize(slab.xstream));
+    if (debug) {
+        for (int p = 0; p < 2; ++p) {
+            float pass_ms = 0.f, xstart = 0.f, xend = 0.f;
+            cudaEvent_t *d = dbg + p * 5;
+            cudaEventElapsedTime(&pass_ms, d[0], d[4]);   // the pass's launches on the main stream
+            cudaEventElapsedTime(&xstart, d[0], d[2]);    // exchange released (boundary bricks done)
+            cudaEventElapsedTime(&xend, d[0], d[3]);      // exchange complete
+            fprintf(stderr, "[sphb200 rank %d] pass %d: launches %.3f ms; exchange released at +%.3f, complete at +%.3f ms\n", slab.rank,
+                    p, pass_ms, xstart, xend);
+        }
+        for (auto &e : dbg) cudaEventDestroy(e);
+    }
     float t[6];
     CKS(cudaEventElapsedTime(&t[0], ev[6], ev[0]));
     for (int k = 0; k < 5; ++k) CKS(cudaEventElapsedTime(&t[k + 1], ev[k], ev[k + 1]));

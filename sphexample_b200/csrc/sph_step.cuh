@@ -122,9 +122,9 @@ __global__ void k_step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, doubl
     ctl->red_disp2 = 0ull;
     ctl->red_visc = 0ull;
     ctl->red_acc2 = 0ull;
-    ctl->work_counter[0] = 0;
-    ctl->work_counter[1] = 0;
-    ctl->work_counter[2] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ctl->work_counter[k] = 0;
+    ctl->bnd_done[0] = ctl->bnd_done[1] = 0;
     ctl->step_open = 1;
     // ---- which kernel serves the two passes of this step ---------------------------------------
     ctl->list_mode[0] = ctl->list_mode[1] = 0;   // LM_CULL
@@ -177,9 +177,8 @@ __global__ void k_invalidate_lists(Ctl *ctl) {
 }
 
 __global__ void k_reset_counters(Ctl *ctl) {
-    ctl->work_counter[0] = 0;
-    ctl->work_counter[1] = 0;
-    ctl->work_counter[2] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ctl->work_counter[k] = 0;
 }
 
 // snapshot of ρₙ for the pass-2 diffusion / viscosity terms (Q2)

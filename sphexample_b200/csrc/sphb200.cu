@@ -190,6 +190,9 @@ class Sim final : public sphb200_sim {
     DevBuf<int> nl_cnt;
     size_t nl_stride = 0;
     int cull_force = 1;   // the cull kernel ignores ctl->list_mode (lists off / stage-level calls)
+    int brick_part = 0;   // which bricks the next interaction launches take: 0 all, 1 slab boundary, 2 interior
+    unsigned *bnd_flag = nullptr;   // slab mode: flag the next interaction launches raise after their boundary bricks
+    unsigned bnd_epoch = 0;
     bool generic = false;
     AxisMap am;
     int ref_major_is_s = 1;
@@ -239,6 +242,10 @@ class Sim final : public sphb200_sim {
     ~Sim() override {
         drop_step_graph();
         if (slab.comm) nccl::api().CommDestroy(slab.comm);
+        if (slab.xstream) cudaStreamDestroy(slab.xstream);
+        if (slab.ev_bnd) cudaEventDestroy(slab.ev_bnd);
+        if (slab.ev_x) cudaEventDestroy(slab.ev_x);
+        if (slab.d_flag) cudaFree(slab.d_flag);
         if (slab.d_counts) cudaFree(slab.d_counts);
         if (slab.h_counts) cudaFreeHost(slab.h_counts);
         if (h_ctl) cudaFreeHost(h_ctl);
@@ -659,8 +666,17 @@ class Sim final : public sphb200_sim {
         k_gather_table<T, D><<<gp, 256, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, perm.p, table(false), table(true), key_tmp.p,
                                                      ccoord.p);
         k_copy_table<T, D><<<gp, 256, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, table(true), table(false));
-        k_build_bricks<D><<<grid_for(row_cap, 128), 128, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, BT, brick_window_limit(),
-                                                                       bricks.p, brick_cap);
+        if (slab.active) {   // boundary-layer bricks first: a pass takes them first and ships their results early
+            k_build_bricks<D><<<grid_for(row_cap, 128), 128, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, BT, brick_window_limit(),
+                                                                           bricks.p, brick_cap, 1);
+            k_mark_boundary_bricks<<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p);
+            k_build_bricks<D><<<grid_for(row_cap, 128), 128, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, BT, brick_window_limit(),
+                                                                           bricks.p, brick_cap, 2);
+            launches += 2;
+        } else {
+            k_build_bricks<D><<<grid_for(row_cap, 128), 128, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, BT, brick_window_limit(),
+                                                                           bricks.p, brick_cap, 0);
+        }
         k_finish_rebuild<<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, count_rebuild);
         launches += 13;
         CK(cudaGetLastError());
@@ -724,7 +740,10 @@ class Sim final : public sphb200_sim {
         g.epilogue = epilogue;
         g.use_tma = opt_tma;
         g.ref_major_is_s = ref_major_is_s;
-        g.counter_slot = pass;
+        g.counter_slot = pass * 3 + brick_part;
+        g.brick_part = brick_part;
+        g.bnd_flag = bnd_flag;
+        g.bnd_epoch = bnd_epoch;
         g.nl = nl.p;
         g.nl_cnt = nl_cnt.p;
         g.nl_stride = nl_stride;
@@ -835,7 +854,7 @@ class Sim final : public sphb200_sim {
             // cull kernel or the list kernel; pass 1 is preceded by the (predicated) list build
             int rc = ensure_lists();
             if (rc) return rc;
-            if (pass == 0 && (rc = generic ? launch_list_build<true>() : launch_list_build<false>())) return rc;
+            if (pass == 0 && brick_part != 2 && (rc = generic ? launch_list_build<true>() : launch_list_build<false>())) return rc;
             if ((rc = launch_cull(pass, epilogue, 0))) return rc;
             if (generic) return pass ? launch_list_t<1, true>(epilogue) : launch_list_t<0, true>(epilogue);
             return pass ? launch_list_t<1, false>(epilogue) : launch_list_t<0, false>(epilogue);
@@ -1005,7 +1024,8 @@ class Sim final : public sphb200_sim {
     int run_steps_slab(int64_t nsteps, bool until_target);
     int slab_exchange_counts(int to_left, int to_right, int *from_left, int *from_right);
     int slab_exchange_records(Table<T, D> from, int sl0, int nl, int sr0, int nr, int dst0, int rl, int rr);
-    int slab_exchange_halo(TA *a, TB *b);
+    int slab_exchange_halo(TA *a, TB *b, cudaStream_t st);
+    int slab_pass(int pass, TA *xa, TB *xb);
     int slab_allreduce_ctl();
     int slab_sort(const SlabFilter &flt, int count_rebuild);
     int slab_rebuild();
