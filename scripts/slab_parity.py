@@ -70,6 +70,14 @@ def run_case(name, make, steps, axis, tol_single, tol_oracle, vel_scale=0.5):
     dist.barrier()
 
 
+if os.environ.get("SLAB_PARITY_QUICK"):   # a short smoke of the exchange / migration / pause paths
+    run_case("dam_break_3d_dp0.02", lambda: util.case_3d_small("float32"), 30, 1, 5e-3, 5e-3)
+    run_case("dam_break_3d_dp0.02_fast", lambda: util.case_3d_small("float64"), 60, 1, 1e-7, 1e-6, vel_scale=3.0)
+    if rank == 0:
+        print("SLAB PARITY", "OK" if all(r["ok"] for r in lines) else "FAILED", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0)
 axes3 = (1, 2)
 for ax in axes3:
     run_case("dam_break_3d_dp0.02", lambda: util.case_3d_small("float64"), 60, ax, 1e-9, 1e-8)

@@ -9,11 +9,12 @@
 //   * every step:      one 5-word all-reduce (max) of the Δt / Δx / |v| reductions + error flag;
 //   * every half step: the two boundary layers' packed state (A, B arrays) to the two neighbours
 //                      — plain contiguous ranges, no pack kernel, because sender and receiver hold
-//                      the layer in the same order (both sort by the same order keys).  A pass is
-//                      ONE launch that takes the bricks of the two boundary layers first; the CTA
-//                      that retires the last of them raises a flag in device memory, on which the
-//                      exchange stream waits (cuStreamWaitValue32) — so the exchange runs while the
-//                      same launch computes the interior bricks;
+//                      the layer in the same order (both sort by the same order keys).  The bricks
+//                      of the two boundary layers are computed first; their exchange then runs on
+//                      a second (high-priority) stream while the interior bricks are computed.
+//                      (Experimental, SPHB200_SLAB_WAITVALUE=1: one launch per pass, the CTA that
+//                      retires the last boundary brick raises a flag on which the exchange stream
+//                      waits with cuStreamWaitValue32.)
 //   * every rebuild:   migration of the particles that left the slab, then the boundary layers'
 //                      full records.
 // NCCL is dlopen()ed (the copy already loaded in the process, e.g. torch's, else libnccl.so.2) so

@@ -77,7 +77,11 @@ int Sim<T, D>::comm_init(const uint8_t *uid, int rank, int world, int axis) {
     {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult qr;
-        if (!getenv("SPHB200_SLAB_SPLIT") &&
+        // EXPERIMENTAL, off by default: the first r1 attempt (exchange enqueued before the launch that
+        // raises the flag) hung on 4 GPUs — presumably NCCL's first-use connection setup synchronises
+        // the stream it is given, which then waits on a flag no launched kernel will raise.  The
+        // order below (launch first) has not been validated on hardware yet.
+        if (getenv("SPHB200_SLAB_WAITVALUE") &&
             cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
             *(void **)(&slab.wait_value32) = fn;
         cudaGetLastError();
@@ -319,12 +323,6 @@ int Sim<T, D>::slab_pass(int pass, TA *xa, TB *xb) {
     if (slab.wait_value32) {
         // one launch: boundary bricks first, the flag releases the exchange, interior bricks go on
         const unsigned epoch = ++slab.epoch;
-        if (slab.wait_value32(slab.xstream, (unsigned long long)(uintptr_t)slab.d_flag, epoch, 0u /* GEQ */) != 0)
-            return fail(SPHB200_ECUDA, "cuStreamWaitValue32 failed");
-        if (dbg) CKS(cudaEventRecord(dbg[2], slab.xstream));
-        if ((rc = slab_exchange_halo(xa, xb, slab.xstream))) return rc;
-        CKS(cudaEventRecord(slab.ev_x, slab.xstream));
-        if (dbg) CKS(cudaEventRecord(dbg[3], slab.xstream));
         bnd_flag = slab.d_flag;
         bnd_epoch = epoch;
         rc = launch_interact(pass, EPI_FUSED);
@@ -334,10 +332,17 @@ int Sim<T, D>::slab_pass(int pass, TA *xa, TB *xb) {
         ++launches;
         if (dbg) CKS(cudaEventRecord(dbg[4], stream));
         if (dbg) CKS(cudaEventRecord(dbg[1], stream));
+        // everything that raises the flag is in flight before anything waits on it
+        if (slab.wait_value32(slab.xstream, (unsigned long long)(uintptr_t)slab.d_flag, epoch, 0u /* GEQ */) != 0)
+            return fail(SPHB200_ECUDA, "cuStreamWaitValue32 failed");
+        if (dbg) CKS(cudaEventRecord(dbg[2], slab.xstream));
+        if ((rc = slab_exchange_halo(xa, xb, slab.xstream))) return rc;
+        CKS(cudaEventRecord(slab.ev_x, slab.xstream));
+        if (dbg) CKS(cudaEventRecord(dbg[3], slab.xstream));
         CKS(cudaStreamWaitEvent(stream, slab.ev_x, 0));
         return SPHB200_OK;
     }
-    // fallback (no stream memory operations): two launches, boundary bricks then interior bricks
+    // default: two launches, boundary bricks then interior bricks (validated on 4 GPUs, profiles/r1q_*)
     brick_part = 1;
     rc = launch_interact(pass, EPI_FUSED);
     if (!rc) {
