@@ -15,6 +15,7 @@
 // which is what a stable sort would have produced — deterministic run to run.
 #pragma once
 
+#include "sph_bricks.h"
 #include "sph_device.cuh"
 
 namespace sph {
@@ -397,55 +398,15 @@ __global__ void k_build_bricks(Ctl *ctl, GridInfo *grid, const int *__restrict__
             int ds = (D == 3) ? (q / 3 - 1) : (q - 1);
             roff[q] = rowbase + (ds * nm + dm) * nx;
         }
-        int out = 0, nb = 0;
-        for (int pass = 0; pass < 2; ++pass) {
-            if (pass == 1) {
-                out = atomicAdd(&grid->nbricks, nb);
-                if (out + nb > brick_cap) {
-                    atomicCAS(&ctl->error, 0, SPH_ERR_ECAPACITY);
-                    break;
-                }
-            }
-            int t0 = p0, cfirst = -1, wlo = 0;
-            for (int cx = 1; cx < nx - 1; ++cx) {          // cells 0 and nx-1 are the empty padding
-                const int cs = cell_start[rowbase + cx], ce = cell_start[rowbase + cx + 1];
-                if (ce <= cs) continue;
-                if (cfirst < 0) {
-                    cfirst = cx;
-                    wlo = 0;
-#pragma unroll
-                    for (int q = 0; q < NR; ++q) wlo += cell_start[roff[q] + cx - 1];
-                } else {
-                    int whi = 0;
-#pragma unroll
-                    for (int q = 0; q < NR; ++q) whi += cell_start[roff[q] + cx + 2];
-                    if (whi - wlo > wlimit && cs > t0) {   // close before this cell
-                        if (pass) bricks[out++] = Brick{t0, cs};
-                        else ++nb;
-                        t0 = cs;
-                        cfirst = cx;
-                        wlo = 0;
-#pragma unroll
-                        for (int q = 0; q < NR; ++q) wlo += cell_start[roff[q] + cx - 1];
-                    }
-                }
-                while (ce - t0 >= bt) {                     // full bricks, possibly ending mid-cell
-                    if (pass) bricks[out++] = Brick{t0, t0 + bt};
-                    else ++nb;
-                    t0 += bt;
-                    cfirst = (t0 < ce) ? cx : -1;          // the next brick starts inside this cell, or afresh
-                    if (cfirst >= 0) {
-                        wlo = 0;
-#pragma unroll
-                        for (int q = 0; q < NR; ++q) wlo += cell_start[roff[q] + cx - 1];
-                    }
-                }
-            }
-            if (t0 < p1) {
-                if (pass) bricks[out++] = Brick{t0, p1};
-                else ++nb;
-            }
+        // two walks of the same deterministic sequence: count, reserve, write
+        int nb = 0;
+        walk_row_bricks<NR>(cell_start, rowbase, nx, roff, bt, wlimit, [&](int, int) { ++nb; });
+        int out = atomicAdd(&grid->nbricks, nb);
+        if (out + nb > brick_cap) {
+            atomicCAS(&ctl->error, 0, SPH_ERR_ECAPACITY);
+            continue;
         }
+        walk_row_bricks<NR>(cell_start, rowbase, nx, roff, bt, wlimit, [&](int t0, int t1) { bricks[out++] = Brick{t0, t1}; });
     }
 }
 

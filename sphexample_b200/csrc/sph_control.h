@@ -1,0 +1,180 @@
+// sph_control.h — the device-resident control block of the step loop and the one-thread logic
+// that advances it.  Plain C++ (host + device): the kernels k_step_control / k_step_end
+// (sph_step.cuh) are thin wrappers, and CPU tests drive the very same code (tests/physics_shim.cpp).
+#pragma once
+
+#include <limits.h>
+#include <math.h>
+#include <string.h>
+
+#include "sph_physics.cuh"
+
+namespace sph {
+
+// ---------------------------------------------------------------------------------------------
+// Device-resident control block: everything the step sequence decides on (Δt, Δx, rebuild,
+// loop termination) lives here so that a whole batch of steps runs without a host round trip.
+// ---------------------------------------------------------------------------------------------
+struct Ctl {
+    // SimulationMetaData fields owned by the loop (src/SPHCellList.jl:679-685)
+    double total_time;
+    double current_dt;
+    double dt, dt2;            // of the step in flight
+    double delta_x;            // rebuild accumulator (src/SPHCellList.jl:739-762)
+    double target_time;        // SimulationLoop's next_output_time
+    long long iteration;
+    long long n_rebuilds;
+    int use_target;            // 1: stop when total_time > target_time
+    int done;                  // set by step_control when the while-condition fails
+    int do_rebuild;            // this step runs UpdateNeighbors!
+    int error;                 // sticky SPHB200_E* code; every kernel returns early when set
+    int step_open;             // step_control ran, step_end has not
+    int pad0;
+    // reductions feeding Δt and Δx (bit patterns of non-negative reals, atomicMax-ed)
+    unsigned long long red_disp2, red_visc, red_acc2;
+    unsigned long long red_err;   // slab mode: max over ranks of -error (all-reduced with the three above)
+    unsigned long long red_vel2;  // max |v|² (bounds the displacement the neighbour lists have to absorb)
+    // work distribution of the interaction kernel
+    int bnd_done[2];           // slab mode: boundary-layer bricks finished in pass 1 / pass 2 of this step
+    int work_counter[8];       // [pass * 3 + part] (part 0 all / 1 boundary / 2 interior bricks); [6]: the list build
+    // per-particle neighbour lists (sph_interact.cuh): which kernel serves each pass of this step
+    int list_mode[2];          // LM_CULL / LM_USE
+    int list_build;            // this step starts with a list build (k_list_build)
+    int list_valid;            // lists exist for the current cell structure
+    int list_fail;             // a build overflowed: bit 0 candidates per brick window, bit 1 entries per particle
+    int list_fail_last;        // the reason of the most recent failed build (diagnostics)
+    int list_off;              // lists are switched off until the next cell rebuild (after a failed build)
+    int n_list_builds;
+    double list_move;          // bound on any particle's displacement since the last list build
+    double list_prev_vmax;     // max |v| at the previous step head
+};
+
+struct GridInfo {
+    int bb_min[3], bb_max[3];  // bounding box of occupied reference cells (inclusive)
+    int cmin[3];               // cell coordinate of grid index 0 per axis (= bb_min - 1)
+    int nx, nm, ns;            // dense grid extents: x fastest, then m, then s (slab axis)
+    int ncell, nrows, nbricks;
+    int nbricks_bnd;           // bricks [0, nbricks_bnd) lie in the first / last owned slab layer (slab mode)
+    int own_row0, own_row1;    // rows [own_row0, own_row1) are owned by this rank (slab mode)
+    int own_p0, own_p1;        // owned particle index range in sorted order
+    int own_l1, own_l2;        // [own_p0, own_l1) = first owned slab layer, [own_l2, own_p1) = last one
+    int n_total;               // particles on this rank (owned + halo)
+};
+
+
+#define SPH_ERR_EINVAL (-1)
+#define SPH_ERR_ECUDA (-2)
+#define SPH_ERR_ESTATE (-3)
+#define SPH_ERR_ECAPACITY (-4)
+#define SPH_ERR_ENCCL (-5)
+#define SPH_ERR_ENUMERIC (-6)
+
+SPH_HD double ctl_bits_to_double(unsigned long long b) {
+    double d;
+#if defined(__CUDA_ARCH__)
+    d = __longlong_as_double((long long)b);
+#else
+    memcpy(&d, &b, 8);
+#endif
+    return d;
+}
+
+// One thread.  Finishes S0/S1, decides S2 (src/SPHCellList.jl:744-762) and the while-condition
+// (:742).  Arithmetic is carried out in T like the reference's (its scalars are ::T).
+// list_skin > 0 switches the per-particle neighbour lists on (sph_interact.cuh): a build pass
+// lists every candidate within H + skin; the lists stay exact while no two particles can have
+// approached by more than skin, i.e. while 2 x (bound on any particle's displacement since the
+// build) <= skin.  The bound: a full step moves a particle by dt (vₙ + vₙ₊₁)/2, at most
+// dt max(vmaxₙ, vmaxₙ₊₁); the half step of pass 2 by dt/2 · vₙ; moving bodies by their prescribed
+// speed (motion_vmax).
+// pause_on_rebuild (slab mode): a rebuild needs the host (exchange sizes), so the step that raises
+// do_rebuild also raises `done`: this step's body and every later enqueued step run empty until the
+// host has rebuilt and resumes the open step — steps can be enqueued in batches without a per-step
+// host round trip and without ever running a step on stale cells.
+template <class T>
+SPH_HD void step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, double list_skin, double motion_vmax, int pause_on_rebuild) {
+    if (ctl->red_err && !ctl->error) ctl->error = -(int)ctl->red_err;   // slab mode: another rank failed
+    ctl->red_err = 0ull;
+    if (ctl->error) return;
+    // consume the reductions unconditionally so that nothing stale survives a skipped step
+    T disp = sph_sqrt((T)ctl_bits_to_double(ctl->red_disp2));
+    T visc = (T)ctl_bits_to_double(ctl->red_visc);
+    T acc2 = (T)ctl_bits_to_double(ctl->red_acc2);
+    const double vmax = fmax(sqrt(ctl_bits_to_double(ctl->red_vel2)), motion_vmax);
+    ctl->red_vel2 = 0ull;
+    ctl->red_disp2 = 0ull;
+    ctl->red_visc = 0ull;
+    ctl->red_acc2 = 0ull;
+    if (ctl->use_target && !(ctl->total_time <= ctl->target_time)) {
+        ctl->done = 1;
+        return;
+    }
+    if (ctl->done) return;
+    ctl->delta_x = (double)((T)ctl->delta_x + T(4) * disp);
+    T dt1 = sph_sqrt(h / sph_sqrt(acc2));   // +inf when every acceleration is zero (first step)
+    T dt2 = h / (c0 + visc);
+    T dt = cfl * sph_min(dt1, dt2);
+    if (!(dt > T(0)) || !(dt < T(1e30))) {
+        ctl->error = SPH_ERR_ENUMERIC;
+        return;
+    }
+    ctl->dt = (double)dt;
+    ctl->dt2 = (double)(dt * T(0.5));
+    if ((T)ctl->delta_x >= h) {
+        ctl->do_rebuild = 1;
+        ctl->delta_x = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            grid->bb_min[k] = INT_MAX;
+            grid->bb_max[k] = INT_MIN;
+        }
+    }
+    ctl->red_disp2 = 0ull;
+    ctl->red_visc = 0ull;
+    ctl->red_acc2 = 0ull;
+    for (int k = 0; k < 8; ++k) ctl->work_counter[k] = 0;
+    ctl->bnd_done[0] = ctl->bnd_done[1] = 0;
+    ctl->step_open = 1;
+    // ---- which kernel serves the two passes of this step ---------------------------------------
+    ctl->list_mode[0] = ctl->list_mode[1] = 0;   // LM_CULL
+    ctl->list_build = 0;
+    if (list_skin > 0.0) {
+        if (ctl->list_fail) {          // the last build overflowed: no lists until the cells change
+            ctl->list_fail_last = ctl->list_fail;
+            ctl->list_fail = 0;
+            ctl->list_valid = 0;
+            ctl->list_off = 1;
+        }
+        if (ctl->do_rebuild) {
+            ctl->list_valid = 0;
+            ctl->list_off = 0;
+        }
+        const double margin = 0.49 * list_skin;
+        const double half = ctl->dt2 * vmax;
+        ctl->list_move += ctl->current_dt * fmax(ctl->list_prev_vmax, vmax);   // the step just completed
+        ctl->list_prev_vmax = vmax;
+        if (!ctl->list_off) {
+            if (ctl->list_valid && ctl->list_move + half <= margin) {
+                ctl->list_mode[0] = ctl->list_mode[1] = 2;          // LM_USE
+            } else {
+                ctl->list_build = 1;                                // k_list_build at xₙ, then both passes use it
+                ctl->list_mode[0] = 2;
+                ctl->list_mode[1] = (half <= margin) ? 2 : 0;
+                ctl->list_move = 0.0;
+                ctl->list_valid = 1;
+                ctl->n_list_builds += 1;
+            }
+        }
+    }
+    if (pause_on_rebuild && ctl->do_rebuild) ctl->done = 1;
+}
+
+// UpdateMetaData!, src/SPHCellList.jl:679-685 (S19)
+SPH_HD void step_end(Ctl *ctl) {
+    if (ctl->error || ctl->done || !ctl->step_open) return;
+    ctl->iteration += 1;
+    ctl->current_dt = ctl->dt;
+    ctl->total_time += ctl->dt;
+    ctl->step_open = 0;
+}
+
+}  // namespace sph

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "sph_bricks.h"
+#include "sph_control.h"
 #include "sph_physics.cuh"
 
 namespace sph {
@@ -66,64 +68,6 @@ template <class T> struct Lay<T, 2> {
 __host__ __device__ __forceinline__ float type_gf(uint8_t t) { return t == 1 ? -1.f : (t == 3 ? 1.f : 0.f); }
 __host__ __device__ __forceinline__ float type_ml(uint8_t t) { return t == 1 ? 1.f : 0.f; }
 
-// ---------------------------------------------------------------------------------------------
-// Device-resident control block: everything the step sequence decides on (Δt, Δx, rebuild,
-// loop termination) lives here so that a whole batch of steps runs without a host round trip.
-// ---------------------------------------------------------------------------------------------
-struct Ctl {
-    // SimulationMetaData fields owned by the loop (src/SPHCellList.jl:679-685)
-    double total_time;
-    double current_dt;
-    double dt, dt2;            // of the step in flight
-    double delta_x;            // rebuild accumulator (src/SPHCellList.jl:739-762)
-    double target_time;        // SimulationLoop's next_output_time
-    long long iteration;
-    long long n_rebuilds;
-    int use_target;            // 1: stop when total_time > target_time
-    int done;                  // set by step_control when the while-condition fails
-    int do_rebuild;            // this step runs UpdateNeighbors!
-    int error;                 // sticky SPHB200_E* code; every kernel returns early when set
-    int step_open;             // step_control ran, step_end has not
-    int pad0;
-    // reductions feeding Δt and Δx (bit patterns of non-negative reals, atomicMax-ed)
-    unsigned long long red_disp2, red_visc, red_acc2;
-    unsigned long long red_err;   // slab mode: max over ranks of -error (all-reduced with the three above)
-    unsigned long long red_vel2;  // max |v|² (bounds the displacement the neighbour lists have to absorb)
-    // work distribution of the interaction kernel
-    int bnd_done[2];           // slab mode: boundary-layer bricks finished in pass 1 / pass 2 of this step
-    int work_counter[8];       // [pass * 3 + part] (part 0 all / 1 boundary / 2 interior bricks); [6]: the list build
-    // per-particle neighbour lists (sph_interact.cuh): which kernel serves each pass of this step
-    int list_mode[2];          // LM_CULL / LM_USE
-    int list_build;            // this step starts with a list build (k_list_build)
-    int list_valid;            // lists exist for the current cell structure
-    int list_fail;             // a build overflowed: bit 0 candidates per brick window, bit 1 entries per particle
-    int list_fail_last;        // the reason of the most recent failed build (diagnostics)
-    int list_off;              // lists are switched off until the next cell rebuild (after a failed build)
-    int n_list_builds;
-    double list_move;          // bound on any particle's displacement since the last list build
-    double list_prev_vmax;     // max |v| at the previous step head
-};
-
-struct GridInfo {
-    int bb_min[3], bb_max[3];  // bounding box of occupied reference cells (inclusive)
-    int cmin[3];               // cell coordinate of grid index 0 per axis (= bb_min - 1)
-    int nx, nm, ns;            // dense grid extents: x fastest, then m, then s (slab axis)
-    int ncell, nrows, nbricks;
-    int nbricks_bnd;           // bricks [0, nbricks_bnd) lie in the first / last owned slab layer (slab mode)
-    int own_row0, own_row1;    // rows [own_row0, own_row1) are owned by this rank (slab mode)
-    int own_p0, own_p1;        // owned particle index range in sorted order
-    int own_l1, own_l2;        // [own_p0, own_l1) = first owned slab layer, [own_l2, own_p1) = last one
-    int n_total;               // particles on this rank (owned + halo)
-};
-
-struct Brick { int t0, t1; };
-
-#define SPH_ERR_EINVAL (-1)
-#define SPH_ERR_ECUDA (-2)
-#define SPH_ERR_ESTATE (-3)
-#define SPH_ERR_ECAPACITY (-4)
-#define SPH_ERR_ENCCL (-5)
-#define SPH_ERR_ENUMERIC (-6)
 
 // ---------------------------------------------------------------------------------------------
 // atomics on non-negative reals via their bit patterns

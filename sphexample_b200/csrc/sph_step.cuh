@@ -69,105 +69,16 @@ __global__ void k_reduce_dt_dx(const typename Lay<T, D>::TA *__restrict__ A, con
     }
 }
 
-// One thread.  Finishes S0/S1, decides S2 (src/SPHCellList.jl:744-762) and the while-condition
-// (:742).  Arithmetic is carried out in T like the reference's (its scalars are ::T).
-// list_skin > 0 switches the per-particle neighbour lists on (sph_interact.cuh): a build pass
-// lists every candidate within H + skin; the lists stay exact while no two particles can have
-// approached by more than skin, i.e. while 2 x (bound on any particle's displacement since the
-// build) <= skin.  The bound: a full step moves a particle by dt (vₙ + vₙ₊₁)/2, at most
-// dt max(vmaxₙ, vmaxₙ₊₁); the half step of pass 2 by dt/2 · vₙ; moving bodies by their prescribed
-// speed (motion_vmax).
-// pause_on_rebuild (slab mode): a rebuild needs the host (exchange sizes), so the step that raises
-// do_rebuild also raises `done`: this step's body and every later enqueued step run empty until the
-// host has rebuilt and resumes the open step — steps can be enqueued in batches without a per-step
-// host round trip and without ever running a step on stale cells.
+// One thread: S0/S1 completion, the S2 decision, the while-condition and the neighbour-list state
+// (sph_control.h holds the logic, shared with the CPU tests).
 template <class T>
 __global__ void k_step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, double list_skin, double motion_vmax,
                                int pause_on_rebuild) {
-    if (ctl->red_err && !ctl->error) ctl->error = -(int)ctl->red_err;   // slab mode: another rank failed
-    ctl->red_err = 0ull;
-    if (ctl->error) return;
-    // consume the reductions unconditionally so that nothing stale survives a skipped step
-    T disp = sph_sqrt((T)bits_to_double(ctl->red_disp2));
-    T visc = (T)bits_to_double(ctl->red_visc);
-    T acc2 = (T)bits_to_double(ctl->red_acc2);
-    const double vmax = fmax(sqrt(bits_to_double(ctl->red_vel2)), motion_vmax);
-    ctl->red_vel2 = 0ull;
-    ctl->red_disp2 = 0ull;
-    ctl->red_visc = 0ull;
-    ctl->red_acc2 = 0ull;
-    if (ctl->use_target && !(ctl->total_time <= ctl->target_time)) {
-        ctl->done = 1;
-        return;
-    }
-    if (ctl->done) return;
-    ctl->delta_x = (double)((T)ctl->delta_x + T(4) * disp);
-    T dt1 = sph_sqrt(h / sph_sqrt(acc2));   // +inf when every acceleration is zero (first step)
-    T dt2 = h / (c0 + visc);
-    T dt = cfl * sph_min(dt1, dt2);
-    if (!(dt > T(0)) || !(dt < T(1e30))) {
-        ctl->error = SPH_ERR_ENUMERIC;
-        return;
-    }
-    ctl->dt = (double)dt;
-    ctl->dt2 = (double)(dt * T(0.5));
-    if ((T)ctl->delta_x >= h) {
-        ctl->do_rebuild = 1;
-        ctl->delta_x = 0.0;
-        for (int k = 0; k < 3; ++k) {
-            grid->bb_min[k] = INT_MAX;
-            grid->bb_max[k] = INT_MIN;
-        }
-    }
-    ctl->red_disp2 = 0ull;
-    ctl->red_visc = 0ull;
-    ctl->red_acc2 = 0ull;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) ctl->work_counter[k] = 0;
-    ctl->bnd_done[0] = ctl->bnd_done[1] = 0;
-    ctl->step_open = 1;
-    // ---- which kernel serves the two passes of this step ---------------------------------------
-    ctl->list_mode[0] = ctl->list_mode[1] = 0;   // LM_CULL
-    ctl->list_build = 0;
-    if (list_skin > 0.0) {
-        if (ctl->list_fail) {          // the last build overflowed: no lists until the cells change
-            ctl->list_fail_last = ctl->list_fail;
-            ctl->list_fail = 0;
-            ctl->list_valid = 0;
-            ctl->list_off = 1;
-        }
-        if (ctl->do_rebuild) {
-            ctl->list_valid = 0;
-            ctl->list_off = 0;
-        }
-        const double margin = 0.49 * list_skin;
-        const double half = ctl->dt2 * vmax;
-        ctl->list_move += ctl->current_dt * fmax(ctl->list_prev_vmax, vmax);   // the step just completed
-        ctl->list_prev_vmax = vmax;
-        if (!ctl->list_off) {
-            if (ctl->list_valid && ctl->list_move + half <= margin) {
-                ctl->list_mode[0] = ctl->list_mode[1] = 2;          // LM_USE
-            } else {
-                ctl->list_build = 1;                                // k_list_build at xₙ, then both passes use it
-                ctl->list_mode[0] = 2;
-                ctl->list_mode[1] = (half <= margin) ? 2 : 0;
-                ctl->list_move = 0.0;
-                ctl->list_valid = 1;
-                ctl->n_list_builds += 1;
-            }
-        }
-    }
-    if (pause_on_rebuild && ctl->do_rebuild) ctl->done = 1;
+    step_control<T>(ctl, grid, h, c0, cfl, list_skin, motion_vmax, pause_on_rebuild);
 }
 
 // UpdateMetaData!, src/SPHCellList.jl:679-685 (S19)
-__global__ void k_step_end(Ctl *ctl) {
-    if (ctl->error || ctl->done || !ctl->step_open) return;
-    ctl->iteration += 1;
-    ctl->current_dt = ctl->dt;
-    ctl->total_time += ctl->dt;
-    ctl->step_open = 0;
-}
+__global__ void k_step_end(Ctl *ctl) { step_end(ctl); }
 
 // any change of positions or cells outside the step sequence voids the neighbour lists
 __global__ void k_invalidate_lists(Ctl *ctl) {

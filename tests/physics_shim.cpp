@@ -74,3 +74,89 @@ extern "C" double shim_eos(const sphb200_params *prm, double rho) {
     Phys<double> ph = phys_from_params<double>(*prm);
     return eos_gamma7(ph, rho);
 }
+
+// ---- brick builder (sphexample_b200/csrc/sph_bricks.h): the product's row walker on host arrays ----
+#include "../sphexample_b200/csrc/sph_bricks.h"
+// cell_start: dense grid of nx * nrows cells (+1), rows of nx cells; nm rows per slab layer.
+// Writes at most cap bricks of row r as (t0, t1) pairs; returns the number of bricks of the row.
+extern "C" int shim_row_bricks(const int *cell_start, int nx, int nm, int dim, int r, int bt, int wlimit, int *out, int cap) {
+    int roff[9];
+    const int nr = dim == 3 ? 9 : 3;
+    const int rowbase = r * nx;
+    for (int q = 0; q < nr; ++q) {
+        int dm = dim == 3 ? (q % 3 - 1) : 0;
+        int ds = dim == 3 ? (q / 3 - 1) : (q - 1);
+        roff[q] = rowbase + (ds * nm + dm) * nx;
+    }
+    int n = 0;
+    auto emit = [&](int t0, int t1) {
+        if (n < cap) { out[2 * n] = t0; out[2 * n + 1] = t1; }
+        ++n;
+    };
+    if (cell_start[rowbase + nx] <= cell_start[rowbase]) return 0;
+    if (dim == 3) walk_row_bricks<9>(cell_start, rowbase, nx, roff, bt, wlimit, emit);
+    else walk_row_bricks<3>(cell_start, rowbase, nx, roff, bt, wlimit, emit);
+    return n;
+}
+
+// the masked (branch-free) fast pair body must equal the guarded one: all pairs, no cut-off test outside
+extern "C" int shim_pair_sums_masked(const sphb200_params *prm, int n, const double *pos, const double *vel, const double *rho,
+                                     const double *press, const double *rho_n, const double *ml, const unsigned char *a_is_i,
+                                     int use_float, double *drho, double *acc) {
+    auto run3 = [&](auto tag) {
+        using T = decltype(tag);
+        constexpr int D = 3;
+        Phys<T> ph = phys_from_params<T>(*prm);
+        for (int a = 0; a < n; ++a) {
+            T fd = T(0), fa[D] = {T(0), T(0), T(0)};
+            T xa[D], va[D];
+            for (int k = 0; k < D; ++k) { xa[k] = (T)pos[a * D + k]; va[k] = (T)vel[a * D + k]; }
+            FastTarget<T> ft = make_fast_target<T>(ph, (T)rho[a], (T)press[a], (T)rho_n[a], (T)ml[a], false);
+            for (int b = 0; b < n; ++b) {
+                T xab[D], vb[D], r2 = T(0);
+                for (int k = 0; k < D; ++k) { xab[k] = xa[k] - (T)pos[b * D + k]; vb[k] = (T)vel[b * D + k]; r2 += xab[k] * xab[k]; }
+                // b == a included on purpose: the self pair contributes exact zeros on the fast path
+                pair_fast<T, D, false, true>(ph, ft, xab, r2, va, vb, (T)rho[b], (T)press[b], (T)rho_n[b], ml[b] > 0.0,
+                                             a_is_i[(size_t)a * n + b] != 0, fd, fa);
+            }
+            drho[a] = (double)fd;
+            for (int k = 0; k < D; ++k) acc[a * D + k] = (double)fa[k];
+        }
+    };
+    if (prm->dim != 3) return -1;
+    if (use_float) run3(float(0)); else run3(double(0));
+    return 0;
+}
+
+// ---- step control (sphexample_b200/csrc/sph_control.h): the product's one-thread logic on the host ----
+#include "../sphexample_b200/csrc/sph_control.h"
+static unsigned long long bits_of(double v) { unsigned long long b; memcpy(&b, &v, 8); return b; }
+// Runs n steps of head (step_control) + body bookkeeping (rebuild clears the request, step_end).  Inputs per
+// step: the reductions the device would have produced (max half-step displacement², visc, |a|², |v|²) and
+// whether the list build of that step overflows.  trace[step] = {dt, do_rebuild, list_build, mode0, mode1,
+// paused, list_move, delta_x, total_time, list_off}.
+extern "C" void shim_control_trace(int n, const double *disp2, const double *visc, const double *acc2, const double *vel2,
+                                   const unsigned char *build_fails, double h, double c0, double cfl, double skin,
+                                   double motion_vmax, int pause, int use_float, double delta_x0, double *trace) {
+    Ctl ctl;
+    GridInfo grid;
+    memset(&ctl, 0, sizeof ctl);
+    memset(&grid, 0, sizeof grid);
+    ctl.delta_x = delta_x0;
+    for (int s = 0; s < n; ++s) {
+        ctl.red_disp2 = bits_of(disp2[s]);
+        ctl.red_visc = bits_of(visc[s]);
+        ctl.red_acc2 = bits_of(acc2[s]);
+        ctl.red_vel2 = bits_of(vel2[s]);
+        if (use_float) step_control<float>(&ctl, &grid, (float)h, (float)c0, (float)cfl, skin, motion_vmax, pause);
+        else step_control<double>(&ctl, &grid, h, c0, cfl, skin, motion_vmax, pause);
+        double *t = trace + (size_t)s * 10;
+        t[0] = ctl.dt; t[1] = ctl.do_rebuild; t[2] = ctl.list_build; t[3] = ctl.list_mode[0]; t[4] = ctl.list_mode[1];
+        t[5] = ctl.done; t[6] = ctl.list_move; t[7] = ctl.delta_x; t[9] = ctl.list_off;
+        if (ctl.done && ctl.do_rebuild) ctl.done = 0;          // the host resumes a paused step after rebuilding
+        if (ctl.do_rebuild) ctl.do_rebuild = 0;                // k_finish_rebuild
+        if (ctl.list_build && build_fails[s]) ctl.list_fail = 2;
+        step_end(&ctl);
+        t[8] = ctl.total_time;
+    }
+}

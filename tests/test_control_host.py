@@ -1,0 +1,114 @@
+"""The product's step-control logic (csrc/sph_control.h, the body of k_step_control / k_step_end),
+driven on the CPU through the shim: Δt, the rebuild trigger (src/SPHCellList.jl:739-762,
+src/TimeStepping.jl:24-46), the neighbour-list state machine and the slab-mode pause."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from test_physics_host import shim  # noqa: F401  (fixture)
+
+H, C0, CFL = 0.0077, 33.14, 0.2
+
+
+def trace(shim, disp, visc, acc2, vel, fails=None, skin=0.0, pause=0, use_float=0, delta_x0=0.0, motion_vmax=0.0):  # noqa: F811
+    n = len(disp)
+    f = lambda a: np.ascontiguousarray(a, np.float64)
+    d2, vi, a2, v2 = f(np.asarray(disp) ** 2), f(visc), f(acc2), f(np.asarray(vel) ** 2)
+    fl = np.ascontiguousarray(np.zeros(n) if fails is None else fails, np.uint8)
+    out = np.zeros((n, 10))
+    shim.shim_control_trace.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_double] * 5 + [C.c_int, C.c_int, C.c_double, C.c_void_p]
+    shim.shim_control_trace(n, d2.ctypes.data, vi.ctypes.data, a2.ctypes.data, v2.ctypes.data, fl.ctypes.data, H, C0, CFL,
+                            skin, motion_vmax, pause, use_float, delta_x0, out.ctypes.data)
+    keys = ("dt", "do_rebuild", "list_build", "mode0", "mode1", "paused", "list_move", "delta_x", "total_time", "list_off")
+    return {k: out[:, i] for i, k in enumerate(keys)}
+
+
+def test_dt_follows_the_reference_formula(shim):  # noqa: F811
+    rng = np.random.default_rng(0)
+    n = 50
+    visc, acc2 = rng.uniform(0, 5, n), rng.uniform(0, 400, n)
+    acc2[0] = 0.0                                           # first step: every acceleration is zero -> dt₁ = +inf (Q3)
+    t = trace(shim, np.zeros(n), visc, acc2, np.zeros(n))
+    dt1 = np.sqrt(H / np.sqrt(acc2, where=acc2 > 0, out=np.full(n, np.nan)))
+    dt1[acc2 == 0] = np.inf
+    ref = CFL * np.minimum(dt1, H / (C0 + visc))            # src/TimeStepping.jl:40-45
+    assert np.allclose(t["dt"], ref, rtol=1e-15)
+    assert t["dt"][0] == pytest.approx(CFL * H / (C0 + visc[0]))
+    assert np.allclose(t["total_time"], np.cumsum(ref), rtol=1e-14)
+
+
+def test_rebuild_when_four_times_the_displacement_reaches_h(shim):  # noqa: F811
+    n = 40
+    disp = np.full(n, 0.03 * H)
+    t = trace(shim, disp, np.zeros(n), np.ones(n), np.zeros(n), delta_x0=1.0 + H)   # SimulationLoop entry: Δx = 1 + h (:739)
+    assert t["do_rebuild"][0] == 1                          # forced rebuild on entry (Q4)
+    # Δx restarts at 0 and grows by 4·disp per step (:723,744): rebuild at the first step where it reaches h
+    acc, expect = 0.0, []
+    for s in range(1, n):
+        acc += 4 * disp[s]
+        hit = acc >= H
+        expect.append(int(hit))
+        if hit:
+            acc = 0.0
+    assert t["do_rebuild"][1:].astype(int).tolist() == expect
+    assert sum(expect) >= 3
+
+
+@pytest.mark.parametrize("use_float", [0, 1])
+def test_lists_are_only_used_inside_their_displacement_bound(shim, use_float):  # noqa: F811
+    rng = np.random.default_rng(1)
+    n = 400
+    vel = np.abs(rng.normal(1.5, 0.8, n)) + 0.1
+    vel[150:170] = 12.0                                      # a burst: the bound must force builds
+    disp = 0.5 * CFL * H / C0 * vel                          # half-step displacement ~ dt/2 · v
+    skin = 0.1 * 2 * H
+    t = trace(shim, disp, np.zeros(n), np.ones(n), vel, skin=skin, use_float=use_float)
+    builds = t["list_build"].astype(int)
+    assert builds[0] == 1 and 3 < builds.sum() < n // 2      # reused, but not forever
+    moved = 0.0                                              # independent bookkeeping of the displacement bound
+    for s in range(n):
+        dt = t["dt"][s]
+        if s > 0:
+            moved += t["dt"][s - 1] * max(vel[s - 1], vel[s])
+        if builds[s] or t["do_rebuild"][s]:
+            assert builds[s] == 1                            # a cell rebuild always rebuilds the lists
+            moved = 0.0
+        half = 0.5 * dt * vel[s]
+        if t["mode0"][s] == 2:
+            assert 2 * moved <= skin * (1 + 1e-12)
+        if t["mode1"][s] == 2:
+            assert 2 * (moved + half) <= skin * (1 + 1e-12)
+        assert t["mode0"][s] == 2                            # pass 1 always has fresh-enough lists (built at xₙ if need be)
+
+
+def test_a_failed_build_switches_lists_off_until_the_cells_change(shim):  # noqa: F811
+    n = 60
+    vel = np.full(n, 1.0)
+    disp = np.full(n, 0.02 * H)                              # rebuild every 13 steps
+    fails = np.zeros(n, np.uint8)
+    fails[0] = 1
+    t = trace(shim, disp, np.zeros(n), np.ones(n), vel, fails=fails, skin=0.2 * H, delta_x0=1.0 + H)
+    first_rebuild = int(np.nonzero(t["do_rebuild"][1:])[0][0]) + 1
+    assert t["list_build"][0] == 1
+    assert np.all(t["list_off"][1:first_rebuild] == 1)
+    assert np.all(t["mode0"][1:first_rebuild] == 0) and np.all(t["list_build"][1:first_rebuild] == 0)
+    assert t["list_build"][first_rebuild] == 1 and t["list_off"][first_rebuild] == 0   # the new cells get a new chance
+
+
+def test_slab_mode_pauses_the_step_that_needs_a_rebuild(shim):  # noqa: F811
+    n = 30
+    disp = np.full(n, 0.05 * H)
+    a = trace(shim, disp, np.zeros(n), np.ones(n), np.zeros(n), pause=0, delta_x0=1.0 + H)
+    b = trace(shim, disp, np.zeros(n), np.ones(n), np.zeros(n), pause=1, delta_x0=1.0 + H)
+    assert np.array_equal(a["do_rebuild"], b["do_rebuild"]) and np.array_equal(a["dt"], b["dt"])
+    assert np.array_equal(b["paused"], b["do_rebuild"])      # paused exactly on rebuild steps ...
+    assert not a["paused"].any()                             # ... and never on one GPU
+    assert np.allclose(a["total_time"], b["total_time"])
+
+
+def test_moving_bodies_count_towards_the_bound(shim):  # noqa: F811
+    n = 100
+    t0 = trace(shim, np.zeros(n), np.zeros(n), np.ones(n), np.zeros(n), skin=0.2 * H)
+    t1 = trace(shim, np.zeros(n), np.zeros(n), np.ones(n), np.zeros(n), skin=0.2 * H, motion_vmax=2.8)
+    assert t0["list_build"].sum() == 1 and t1["list_build"].sum() > 3

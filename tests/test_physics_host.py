@@ -90,6 +90,30 @@ def test_fast_pair_body_matches_oracle(oracle_lib, shim, dim, pass2):
     assert util.relerr(acc, o.get("acc")) < 1e-12
 
 
+@pytest.mark.parametrize("use_float,tol", [(False, 1e-12), (True, 2e-4)])
+def test_masked_pair_body_equals_the_guarded_one(oracle_lib, shim, use_float, tol):
+    """the list kernel's branch-free body (kernel-gradient factor zeroed outside H, self pair and
+    far pairs included) sums to the same result as the cut-off-guarded body"""
+    case = util.perturb(util.case_3d_small())
+    parts = _subset(case, 700, np.array([0.0, 0.0, 0.0]), np.array([0.2, 0.2, 0.16]))
+    p = util.params_of(case)
+    o = oracle_lib.Oracle(p, parts)
+    o.update_neighbors()
+    o.pressure(0)
+    o.neighbor_loop(0)
+    n = len(parts)
+    pos, vel, rho, press = o.get("pos"), o.get("vel"), o.get("rho"), o.get("press")
+    ml = (o.types == 1).astype(np.float64)
+    roles = _roles(o.cells, n)
+    drho, acc = np.zeros(n), np.zeros((n, 3))
+    shim.shim_pair_sums_masked.argtypes = [C.POINTER(_abi.Params), C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p, C.c_void_p]
+    rc = shim.shim_pair_sums_masked(C.byref(p), n, _ptr(pos), _ptr(vel), _ptr(rho), _ptr(press), _ptr(rho), _ptr(ml),
+                                    _ptr(roles), int(use_float), _ptr(drho), _ptr(acc))
+    assert rc == 0 and np.all(np.isfinite(drho)) and np.all(np.isfinite(acc))
+    assert util.relerr(drho, o.get("drhodt")) < tol
+    assert util.relerr(acc, o.get("acc")) < tol
+
+
 @pytest.mark.parametrize("dim", [2, 3])
 def test_fast_pair_body_fp32_tolerance(oracle_lib, shim, dim):
     o, drho, acc, _ = _run_case(oracle_lib, shim, dim, _set(), generic=False, use_float=True)
