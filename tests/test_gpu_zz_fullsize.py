@@ -1,0 +1,117 @@
+"""BASELINE.json's full single-GPU size (C3: the 3D dam break at ~1 M particles, fp32) through the
+C-ABI: direct parity against the oracle where it finishes in seconds (one rebuild, one pass, a few
+steps) and size-independent properties (sortedness, permutation checksums, idempotence, momentum
+conservation, list path = cull path).  Named zz so that it runs after the small-case suites."""
+import numpy as np
+import pytest
+
+import util
+from sphexample_b200 import cases
+from sphexample_b200.simulation import Simulation
+
+pytestmark = pytest.mark.gpu
+
+N_TARGET = 1_000_000
+
+
+@pytest.fixture(scope="module")
+def c3():
+    dp = cases.dp_for_count_3d(N_TARGET)
+    case = cases.case_dam_break_3d(dp, "float32")
+    # a smooth, moderate velocity field so that every pair term is exercised (as util.perturb, without jitter)
+    P = case.particles
+    f = (P.Type == 1)
+    x = P.Position.astype(np.float64)
+    P.Velocity[:, 0] = (0.5 * np.sin(3.0 * x[:, 2] + 1.0) * f).astype(np.float32)
+    P.Velocity[:, 2] = (-0.5 * np.cos(2.0 * x[:, 0]) * f).astype(np.float32)
+    return case
+
+
+def test_cell_sort_properties_at_full_size(c3):
+    p = util.params_of(c3)
+    sim = Simulation(p)
+    sim.upload(c3.particles)
+    n = len(c3.particles)
+    ic = sim.UpdateNeighbors()
+    st = sim.download(fields=("ID", "Cells", "Position", "Type"))
+    # a permutation of the input: checksums of the identity column
+    ids = st["ID"]
+    assert ids.shape[0] == n and int(ids.sum()) == int(c3.particles.ID.astype(np.int64).sum())
+    assert int(np.bitwise_xor.reduce(ids)) == int(np.bitwise_xor.reduce(c3.particles.ID.astype(np.int64)))
+    assert np.array_equal(np.sort(ids), np.sort(c3.particles.ID.astype(np.int64)))
+    # sorted by cell in the reference's order: last dimension most significant (CartesianIndex order)
+    c = st["Cells"]
+    key = (c[:, 2] - c[:, 2].min()) * (1 << 40) + (c[:, 1] - c[:, 1].min()) * (1 << 20) + (c[:, 0] - c[:, 0].min())
+    assert np.all(np.diff(key) >= 0)
+    # stable: inside a cell the previous (= ID) order is kept
+    same = np.diff(key) == 0
+    assert np.all(np.diff(ids)[same] > 0)
+    # the cell of every particle is map_floor of its position (src/SPHCellList.jl:56-61)
+    xs = st["Position"].astype(np.float64)
+    ref_cells = (np.sign(xs) * np.trunc(np.abs(xs) * p.H_inv + 0.5)).astype(np.int64)
+    assert np.array_equal(ref_cells, c)
+    # occupied cells + 1 = IndexCounter; cell ranges tile [0, N)
+    cells, start = sim.cell_list()
+    assert ic == len(cells) + 1 and start[0] == 0 and start[-1] == n and np.all(np.diff(start) > 0)
+    # idempotent: a rebuild of the sorted table changes nothing
+    sim.UpdateNeighbors()
+    assert np.array_equal(sim.download(fields=("ID",))["ID"], ids)
+    sim.close()
+
+
+def test_one_pass_matches_oracle_at_full_size(oracle_lib, c3):
+    p = util.params_of(c3)
+    sim = Simulation(p)
+    sim.upload(c3.particles)
+    o = oracle_lib.Oracle(p, c3.particles, nthreads=oracle_lib.max_threads())
+    assert sim.UpdateNeighbors() == o.update_neighbors()
+    assert np.array_equal(sim.download(fields=("ID",))["ID"], o.ids)
+    sim.Pressure(0)
+    o.pressure(0)
+    d, a = sim.NeighborLoop(0)
+    o.neighbor_loop(0)
+    util.check(util.relerr(d, o.get("drhodt")), 2e-4)
+    util.check(util.relerr(a, o.get("acc")), 2e-4)
+    # momentum: every pair force is applied with opposite signs to its two ends (equal masses)
+    a64 = a.astype(np.float64)
+    util.check(float(np.abs(a64.sum(0)).max() / np.abs(a64).sum(0).max()), 1e-4)
+    o.close()
+    sim.close()
+
+
+def test_fused_steps_match_oracle_at_full_size(oracle_lib, c3):
+    p = util.params_of(c3)
+    sim = Simulation(p)
+    sim.upload(c3.particles)
+    o = oracle_lib.Oracle(p, c3.particles, nthreads=oracle_lib.max_threads())
+    rep = sim.step(6, reset_delta_x=True)
+    o.step(6, True)
+    orep = o.report()
+    assert rep["iteration"] == orep["iteration"] == 6
+    assert rep["total_time"] == pytest.approx(orep["total_time"], rel=1e-5)
+    st = sim.download(order="id")
+    ids = o.ids
+    assert np.all(np.isfinite(st["Velocity"])) and np.all(np.isfinite(st["Density"]))
+    util.check(util.relerr(st["Position"], util.by_id(ids, o.get("pos"))), 2e-6)
+    util.check(util.relerr(st["Velocity"], util.by_id(ids, o.get("vel"))), 5e-3)
+    util.check(util.relerr(st["Density"], util.by_id(ids, o.get("rho"))), 1e-5)
+    o.close()
+    sim.close()
+
+
+def test_list_path_equals_cull_path_at_full_size(c3):
+    out = {}
+    for lists in (0, 1):
+        sim = Simulation(util.params_of(c3))
+        sim.set_option("lists", lists)
+        sim.upload(c3.particles)
+        rep = sim.step(12, reset_delta_x=True)
+        out[lists] = (rep, sim.download(order="id", fields=("Position", "Velocity", "Density", "ID")), sim.stat("list_builds"),
+                      sim.stat("list_off"))
+        sim.close()
+    (r0, s0, b0, _), (r1, s1, b1, off1) = out[0], out[1]
+    assert b0 == 0 and 1 <= b1 < 12 and off1 == 0            # the lists were built, reused and never overflowed
+    assert r0["iteration"] == r1["iteration"] == 12
+    assert np.array_equal(s0["ID"], s1["ID"])
+    for f in ("Position", "Velocity", "Density"):
+        util.check(util.relerr(s1[f], s0[f]), 2e-4)
