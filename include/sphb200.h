@@ -144,7 +144,8 @@ int sphb200_set_stream(sphb200_sim *sim, void *cuda_stream);
  * "smem_kb" (shared memory per CTA of the cull kernel), "batch" (steps per host sync),
  * "generic" (1 = force the run-time-dispatched pair body), "lists" (0/1 per-particle neighbour
  * lists reused across passes), "skin" (list skin as a fraction of H), "lcap" (list entries per
- * particle), "list_smem_kb" (shared memory per CTA of the list kernel), "graph" (0/1 replay one
+ * particle), "list_smem_kb" (shared memory per CTA of the list kernel), "list_order" (0/1 bank-aware
+ * order of the list entries; experimental), "graph" (0/1 replay one
  * captured CUDA graph per step instead of ~25 launches) */
 int sphb200_set_option(sphb200_sim *sim, const char *name, double value);
 /* run-time counters: "list_builds", "list_off" (1 = lists switched off after an overflow),

@@ -23,6 +23,7 @@
 #include <type_traits>
 
 #include "sph_device.cuh"
+#include "sph_listorder.h"
 
 namespace sph {
 
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
 // the particle's list in global memory.  Runs when k_step_control raises ctl->list_build, on the
 // state-n positions, before pass 1 of that step.
 // =================================================================================================
-template <class T, int D, bool GENERIC, int BT>
+template <class T, int D, bool GENERIC, int BT, bool ORDER = false>
 __global__ void __launch_bounds__(BT) k_list_build(const InteractArgs<T, D> g) {
     using L = Lay<T, D>;
     using TA = typename L::TA;
@@ -509,6 +510,7 @@ __global__ void __launch_bounds__(BT) k_list_build(const InteractArgs<T, D> g) {
     // per-thread append buffer slist[k * BT + tid] (LIST_CAP entries): accepted candidates are
     // appended branch-free and leave for global memory 8 at a time as 16-byte stores
     unsigned short *slist = reinterpret_cast<unsigned short *>(smem_raw + (size_t)cap * esA);
+    unsigned short *slist2 = slist + LIST_CAP * BT;   // scratch column of the bank-aware ordering (list_order only)
 
     __shared__ uint64_t s_bar;
     __shared__ int s_brick;
@@ -591,10 +593,18 @@ __global__ void __launch_bounds__(BT) k_list_build(const InteractArgs<T, D> g) {
         auto flush = [&](bool final) {
             const int cnt = (int)((waddr - waddr0) / (uint32_t)(BT * 2));
             const int nchunks = final ? ((cnt + 7) >> 3) : (cnt >> 3);
+            const int m = final ? cnt : nchunks * 8;   // entries that leave now
+            BankRotator rot;
+            auto in = [&](int k) -> unsigned { return (unsigned)slist[k * BT + tid]; };
+            auto tmp = [&](int p) -> unsigned short & { return slist2[p * BT + tid]; };
+            if (ORDER) rot.prepare(m, tid, in, tmp);
             for (int c = 0; c < nchunks; ++c) {
                 unsigned e[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) e[u] = (c * 8 + u < cnt) ? (unsigned)slist[(c * 8 + u) * BT + tid] : (unsigned)total;
+                for (int u = 0; u < 8; ++u) {
+                    const int k = c * 8 + u;
+                    e[u] = (k < m) ? (ORDER ? rot.pull(k, tmp) : in(k)) : (unsigned)total;
+                }
                 if (lcount + 8 <= lcap && valid)
                     gl[(size_t)(lcount >> 3) * g.nl_stride] =
                         make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));

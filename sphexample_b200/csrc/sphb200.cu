@@ -185,6 +185,7 @@ class Sim final : public sphb200_sim {
     // options
     int opt_compact, opt_tma, opt_smem_kb, opt_batch;
     int opt_lists, opt_lcap, opt_list_smem_kb;   // per-particle neighbour lists (sph_interact.cuh)
+    int opt_list_order;                          // bank-aware entry order (sph_listorder.h); off until validated on hardware
     double opt_skin;                             // list skin as a fraction of H
     DevBuf<uint4> nl;
     DevBuf<int> nl_cnt;
@@ -235,6 +236,7 @@ class Sim final : public sphb200_sim {
         opt_lcap = env_int("SPHB200_LCAP", D == 3 ? 320 : 96);
         opt_list_smem_kb = env_int("SPHB200_LIST_SMEM_KB", 72);   // 3 CTAs per SM (r1 sweep: 56 / 72 / 100 KB -> 0.81 / 0.69 / 0.80 ms per pass)
         opt_skin = env_int("SPHB200_SKIN_PCT", 10) * 0.01;
+        opt_list_order = env_int("SPHB200_LIST_ORDER", 0);
         am.ax_s = D - 1;   // default: the reference's most significant axis
         am.ax_m = (D == 3) ? 1 : 0;
         build_phys();
@@ -328,6 +330,7 @@ class Sim final : public sphb200_sim {
         else if (k == "skin") opt_skin = value;
         else if (k == "lcap") opt_lcap = std::max(8, ((int)value + 7) & ~7);
         else if (k == "list_smem_kb") opt_list_smem_kb = (int)value;
+        else if (k == "list_order") opt_list_order = (int)value;
         else return fail(SPHB200_EINVAL, "unknown option '%s'", k.c_str());
         return SPHB200_OK;
     }
@@ -788,8 +791,12 @@ class Sim final : public sphb200_sim {
     // the physics-free list build (runs only when k_step_control raised ctl->list_build)
     template <bool GEN>
     int launch_list_build() {
-        auto kern = k_list_build<T, D, GEN, BT>;
-        const int list_bytes = LIST_CAP * BT * 2;
+        return opt_list_order ? launch_list_build_t<GEN, true>() : launch_list_build_t<GEN, false>();
+    }
+    template <bool GEN, bool ORDER>
+    int launch_list_build_t() {
+        auto kern = k_list_build<T, D, GEN, BT, ORDER>;
+        const int list_bytes = LIST_CAP * BT * 2 * (ORDER ? 2 : 1);   // append buffer (+ ordering scratch)
         int smem = std::min(opt_smem_kb, 200) * 1024;
         int cap = std::min(((smem - 64) / (int)sizeof(TA)) & ~3, 32764);
         smem = cap * (int)sizeof(TA) + list_bytes;

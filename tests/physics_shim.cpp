@@ -160,3 +160,14 @@ extern "C" void shim_control_trace(int n, const double *disp2, const double *vis
         t[8] = ctl.total_time;
     }
 }
+
+// ---- bank-aware list ordering (sphexample_b200/csrc/sph_listorder.h) ----
+#include "../sphexample_b200/csrc/sph_listorder.h"
+// reorders entries[0..m) (m <= 64) for lane q exactly as k_list_build's flush does; returns pulls done
+extern "C" int shim_bank_rotate(const unsigned short *entries, int m, int q, unsigned short *out) {
+    unsigned short tmp[64];
+    BankRotator rot;
+    rot.prepare(m, q, [&](int k) -> unsigned { return entries[k]; }, [&](int p) -> unsigned short & { return tmp[p]; });
+    for (int k = 0; k < m; ++k) out[k] = (unsigned short)rot.pull(k, [&](int p) -> unsigned short & { return tmp[p]; });
+    return m;
+}

@@ -115,3 +115,27 @@ def test_list_path_equals_cull_path_at_full_size(c3):
     assert np.array_equal(s0["ID"], s1["ID"])
     for f in ("Position", "Velocity", "Density"):
         util.check(util.relerr(s1[f], s0[f]), 2e-4)
+
+
+@pytest.mark.parametrize("name", ["c1_2d_f64", "3d_f32"])
+def test_bank_ordered_lists_give_the_same_physics(name):
+    """list_order=1 (experimental, csrc/sph_listorder.h): the build hands each lane its entries in a
+    bank-friendly order; only the summation order may change"""
+    mk = {"c1_2d_f64": lambda: util.case_c1("float64"), "3d_f32": lambda: util.case_3d_small("float32")}[name]
+    out = {}
+    for order in (0, 1):
+        case = util.perturb(mk(), vel_scale=2.0)
+        sim = Simulation(util.params_of(case))
+        sim.set_option("lists", 1)
+        sim.set_option("list_order", order)
+        sim.upload(case.particles)
+        rep = sim.step(80, reset_delta_x=True)
+        out[order] = (rep, sim.download(order="id", fields=("Position", "Velocity", "Density")), sim.stat("list_builds"),
+                      sim.stat("list_off"))
+        sim.close()
+    (r0, s0, b0, off0), (r1, s1, b1, off1) = out[0], out[1]
+    assert b0 == b1 >= 2 and off0 == off1 == 0
+    assert r0["n_rebuilds"] == r1["n_rebuilds"]
+    tol = 1e-11 if name.endswith("f64") else 2e-4
+    for f in ("Position", "Velocity", "Density"):
+        util.check(util.relerr(s1[f], s0[f]), tol)
