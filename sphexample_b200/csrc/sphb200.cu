@@ -961,6 +961,7 @@ class Sim final : public sphb200_sim {
     }
     int enqueue_step() {
         int rc;
+        if ((rc = ensure_lists())) return rc;   // any (re)allocation happens outside a stream capture
         // (the legacy default stream cannot be captured: callers that hand it over via set_stream get plain launches)
         if (!opt_graph || !have_half || !have_cells || stream == nullptr) {   // first steps: arguments still change, attributes get set
             if ((rc = enqueue_step_head())) return rc;
