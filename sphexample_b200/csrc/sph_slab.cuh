@@ -42,6 +42,7 @@ struct Api {
     int (*GetUniqueId)(UniqueId *) = nullptr;
     int (*CommInitRank)(comm_t *, int, UniqueId, int) = nullptr;
     int (*CommDestroy)(comm_t) = nullptr;
+    int (*CommAbort)(comm_t) = nullptr;   // optional
     int (*Send)(const void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
@@ -81,6 +82,7 @@ struct Api {
         SPH_NCCL_SYM(GroupEnd, "ncclGroupEnd")
         SPH_NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef SPH_NCCL_SYM
+        *(void **)(&CommAbort) = dlsym(lib, "ncclCommAbort");
         return true;
     }
 };
@@ -93,6 +95,7 @@ inline Api &api() {
 
 struct SlabComm {
     bool active = false;
+    bool dead = false;              // a wait timed out: the communicator is aborted, not destroyed, on teardown
     int rank = 0, world = 1;
     int left = -1, right = -1;      // neighbour ranks along the slab axis (-1: domain end)
     nccl::comm_t comm = nullptr;

@@ -154,7 +154,10 @@ int Sim<T, D>::slab_exchange_counts(int to_left, int to_right, int *from_left, i
     }
     NCK(nccl::api().GroupEnd());
     CKS(cudaMemcpyAsync(slab.h_counts, slab.d_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
-    CKS(cudaStreamSynchronize(stream));
+    {
+        int rcw = wait_stream();
+        if (rcw) return rcw;
+    }
     *from_left = slab.h_counts[2];
     *from_right = slab.h_counts[3];
     return SPHB200_OK;

@@ -14,7 +14,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <numeric>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -243,7 +245,10 @@ class Sim final : public sphb200_sim {
     }
     ~Sim() override {
         drop_step_graph();
-        if (slab.comm) nccl::api().CommDestroy(slab.comm);
+        if (slab.comm) {
+            if (!slab.dead) nccl::api().CommDestroy(slab.comm);
+            else if (nccl::api().CommAbort) nccl::api().CommAbort(slab.comm);
+        }
         if (slab.xstream) cudaStreamDestroy(slab.xstream);
         if (slab.ev_bnd) cudaEventDestroy(slab.ev_bnd);
         if (slab.ev_x) cudaEventDestroy(slab.ev_x);
@@ -590,11 +595,35 @@ class Sim final : public sphb200_sim {
     int64_t num_particles() const override { return slab.active ? slab.own_p1 - slab.own_p0 : n; }
     int64_t launch_count() const override { return launches; }
 
+    // Wait for the stream.  In slab mode the stream carries NCCL operations whose completion depends
+    // on the other ranks: instead of blocking forever behind a dead or diverged peer, poll with a
+    // deadline (SPHB200_SLAB_TIMEOUT_S, default 600) and fail loudly.
+    int wait_stream() {
+        if (!slab.active) {
+            CK(cudaStreamSynchronize(stream));
+            return SPHB200_OK;
+        }
+        const double limit_s = (double)env_int("SPHB200_SLAB_TIMEOUT_S", 600);
+        const auto t0 = std::chrono::steady_clock::now();
+        for (long spins = 0;; ++spins) {
+            cudaError_t e = cudaStreamQuery(stream);
+            if (e == cudaSuccess) return SPHB200_OK;
+            if (e != cudaErrorNotReady)
+                return fail(SPHB200_ECUDA, "cudaStreamQuery failed: %s (%s:%d)", cudaGetErrorString(e), __FILE__, __LINE__);
+            if (spins > 4000) {   // the common case completes within the busy spins
+                const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                if (el > limit_s) slab.dead = true;
+                if (el > limit_s)
+                    return fail(SPHB200_ENCCL, "rank %d: no progress for %.0f s in a slab-mode wait (a peer rank died or the ranks diverged)",
+                                slab.rank, el);
+                std::this_thread::sleep_for(std::chrono::microseconds(20));
+            }
+        }
+    }
     int sync_ctl() {
         CK(cudaMemcpyAsync(h_ctl, d_ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
         CK(cudaMemcpyAsync(h_grid, d_grid.p, sizeof(GridInfo), cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
-        return SPHB200_OK;
+        return wait_stream();
     }
     int push_ctl() {
         CK(cudaMemcpyAsync(d_ctl.p, h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
