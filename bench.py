@@ -397,6 +397,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # watchdog: a wedged run (a peer rank died, a collective never completes) must end, not hang its caller
+    limit = float(os.environ.get("SPHB200_BENCH_TIMEOUT_S", "1500"))
+
+    def _expired():
+        sys.stderr.write(f"bench.py: rank {rank} exceeded {limit:.0f} s, giving up\n")
+        sys.stderr.flush()
+        os._exit(3)
+    wd = threading.Timer(limit, _expired)
+    wd.daemon = True
+    wd.start()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
