@@ -1,23 +1,31 @@
-// sph_interact.cuh — the fused neighbour-traversal kernel: NeighborLoop! ∘ ComputeInteractions!
+// sph_interact.cuh — the pair traversal: NeighborLoop! ∘ ComputeInteractions!
 // (src/SPHCellList.jl:168-217,268-317) as a GATHER over the full 3^D stencil, with the
-// symplectic half/full updates (src/SPHCellList.jl:624-677) fused into its epilogue.
+// symplectic half/full updates (src/SPHCellList.jl:624-677) fused into the epilogue.
+// No atomics, no per-thread accumulator copies (ResetStep!/ReductionStep!, :367-484, vanish).
 //
 // Work unit = one "brick": up to BT consecutive (cell-sorted) particles of one row of cells.
 // Because x is the fastest key component, the candidates of a brick are, for each of the
-// 3^(D-1) neighbouring rows, ONE contiguous span of the sorted arrays (cells cx0-1 .. cx1+1):
-//   * one elected thread stages those 9 (3 in 2D) spans of each packed array into shared memory
-//     with cp.async.bulk (1-D TMA) completing on an mbarrier;
-//   * each thread owns one target particle; a warp walks the union of its lanes' windows with
-//     broadcast shared-memory reads and tests the cut-off (phase 1, cheap, ~18 % hit rate in 3D);
-//   * accepted neighbours are appended to a per-thread list in shared memory and the ~70-flop
-//     pair body runs afterwards over the lists (phase 2), so the expensive body executes on
-//     densely populated warps instead of under an 18 %-full predicate mask;
-//   * no atomics, no per-thread accumulator copies (ResetStep!/ReductionStep!, :367-484, vanish).
-// Persistent CTAs fetch bricks from an atomic work counter.
+// 3^(D-1) neighbouring rows, ONE contiguous span of the sorted arrays (cells cx0-1 .. cx1+1);
+// one elected thread stages those 9 (3 in 2D) spans of each packed array into shared memory with
+// cp.async.bulk (1-D TMA) completing on an mbarrier.  Persistent CTAs fetch bricks from an atomic
+// work counter.  Three kernels share this frame:
+//
+//   k_interact       the CULL kernel: each thread owns one target particle; a warp walks the union
+//                    of its lanes' windows with broadcast shared-memory reads, tests the cut-off
+//                    (~18 % hit rate in 3D) and runs the pair body in place, or (COMPACT) from
+//                    per-thread lists in shared memory so that the body executes on dense warps.
+//   k_list_build     the same walk without physics: records, per particle, every candidate inside
+//                    the window and within H + skin as (window index | role) in global memory.
+//   k_interact_list  stages the brick's whole window and runs the pair body over the recorded
+//                    entries only (~190 instead of ~770 candidates), branch-free.
+//
+// ctl->list_mode[pass] (k_step_control) says which of k_interact / k_interact_list serves a pass;
+// the other one returns at once.
 //
 // Pair-set fidelity: a candidate b is evaluated for target a iff b's (stale) cell is within the
 // 3^D stencil of a's (stale) cell AND |x_a - x_b|² <= H² now — exactly the reference's set,
-// including its misses between rebuilds — hence the per-lane window test.
+// including its misses between rebuilds — hence the per-lane window test (applied by the cull walk
+// and by the list build; cells do not change while a list lives).
 #pragma once
 
 #include <type_traits>
