@@ -115,6 +115,45 @@ class SlabDecomposition:
         self.sim.upload(self.parts.permuted(self.mine))
         return self
 
+    def imbalance(self) -> float:
+        """max / mean of the owned particle counts over the ranks (collective)"""
+        import torch.distributed as dist
+        n = int(self.sim.num_particles)
+        if self.world == 1:
+            return 1.0
+        counts = [None] * self.world
+        dist.all_gather_object(counts, n)
+        return max(counts) / (sum(counts) / len(counts))
+
+    def rebalance(self, threshold: float = 1.15) -> bool:
+        """Re-plan the slab edges from the CURRENT particle distribution when the ranks' loads have
+        drifted apart by more than `threshold` (max / mean), and redistribute.  Collective; goes
+        through the host (download, all-gather, upload) — meant for the rare re-plan of a long run,
+        not for the step loop, whose migration only ever moves particles between adjacent slabs.
+        The simulation clock is carried over.  Returns whether a re-plan happened."""
+        import torch.distributed as dist
+        from .preprocess import make_particles
+        if self.world == 1 or self.imbalance() <= threshold:
+            return False
+        rep = self.sim.report()
+        st = self.sim.download(fields=("Position", "Velocity", "Acceleration", "Density", "ID", "Type", "GroupMarker"))
+        parts = [None] * self.world
+        dist.all_gather_object(parts, st)
+        cat = {k: np.concatenate([p[k] for p in parts]) for k in st}
+        coords = cell_coord(cat["Position"][:, self.axis], self.H_inv)
+        self.edges = plan_edges(coords, self.world)
+        mine = np.nonzero(owner_of(coords, self.edges) == self.rank)[0]
+        mine = mine[np.argsort(cat["ID"][mine], kind="stable")]          # the table is kept in ascending ID order
+        sub = make_particles(cat["Position"][mine], cat["Density"][mine], cat["Type"][mine], cat["GroupMarker"][mine],
+                             cat["ID"][mine], velocity=cat["Velocity"][mine], dtype=cat["Position"].dtype, sort_by_id=False)
+        sub.Acceleration[:] = cat["Acceleration"][mine]
+        lo, hi = slab_bounds(self.edges, self.rank)
+        self.sim.set_slab(lo, hi)
+        self.sim.upload(sub)
+        self.sim.set_time(rep["total_time"], rep["iteration"])
+        self.n_owned = int(mine.size)
+        return True
+
     def gather(self, order: str = "id", fields=("Position", "Velocity", "Density", "Pressure", "ID")):
         """All ranks' owned particles on rank 0 (None elsewhere)."""
         import torch.distributed as dist
