@@ -119,6 +119,8 @@ def test_list_path_equals_cull_path_at_full_size(c3):
         util.check(util.relerr(s1[f], s0[f]), 2e-4)
 
 
+@pytest.mark.xfail(reason="list_order is experimental and off by default: written after round 1's GPU budget was spent, "
+                          "never run on hardware (CPU tests cover its ordering logic); an XPASS here validates it", strict=False)
 @pytest.mark.parametrize("name", ["c1_2d_f64", "3d_f32"])
 def test_bank_ordered_lists_give_the_same_physics(name):
     """list_order=1 (experimental, csrc/sph_listorder.h): the build hands each lane its entries in a
