@@ -164,3 +164,26 @@ def test_step_graph_replay_is_bitwise_identical_to_plain_launches(name):
     assert r0["total_time"] == r1["total_time"]
     for f in ("Position", "Velocity", "Density", "Pressure"):
         assert np.array_equal(s0[f], s1[f]), f
+
+
+@pytest.mark.parametrize("name,mk", [("c1_2d", lambda: util.case_c1("float64")), ("3d_small", lambda: util.case_3d_small("float64")),
+                                     ("c5_mdbc", lambda: util.case_c5("float64"))])
+def test_gpu_matches_the_committed_oracle_outputs(name, mk):
+    """GPU fp64 against tests/golden/oracle_*.npz (the oracle's outputs on the shipped layouts at a
+    fixed step, frozen by tests/golden/make_oracle_golden.py) — no oracle in the loop"""
+    import os
+    g = np.load(os.path.join(util.GOLDEN, f"oracle_{name}.npz"))
+    case = mk()
+    sim = Simulation(util.params_of(case))
+    sim.upload(case.particles)
+    rep = sim.step(int(g["steps"]), reset_delta_x=True)
+    st = sim.download(order="id")
+    sim.close()
+    where = {int(i): k for k, i in enumerate(st["ID"])}
+    pick = np.array([where[int(i)] for i in g["ids"]])
+    assert rep["n_rebuilds"] == int(g["n_rebuilds"])
+    assert rep["total_time"] == pytest.approx(float(g["total_time"]), rel=1e-12)
+    util.check(util.relerr(st["Density"][pick], g["rho"]), 1e-10)
+    util.check(util.relerr(st["Velocity"][pick], g["vel"]), 1e-8)
+    util.check(util.relerr(st["Position"][pick], g["pos"]), 1e-12)
+    util.check(util.relerr(st["Pressure"][pick], g["press"]), 1e-6)

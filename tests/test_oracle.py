@@ -138,3 +138,30 @@ def test_threads_do_not_change_cell_list_or_state(oracle_lib):
     assert np.array_equal(a.ids, b.ids)
     assert util.relerr(a.get("rho"), b.get("rho")) < 1e-13
     assert util.relerr(a.get("vel"), b.get("vel")) < 1e-11
+
+
+@pytest.mark.parametrize("name", ["c1_2d", "3d_small", "c5_mdbc"])
+def test_oracle_reproduces_its_committed_outputs(oracle_lib, name):
+    """tests/golden/oracle_*.npz (made by tests/golden/make_oracle_golden.py): the restatement's own
+    outputs on the shipped layouts at a fixed step, frozen against drift; any thread count must
+    reproduce them to rounding"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_oracle_golden", os.path.join(util.GOLDEN, "make_oracle_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(util.GOLDEN, f"oracle_{name}.npz"))
+    mk, steps = mod.CASES[name]
+    assert steps == int(g["steps"])
+    case = mk()
+    o = oracle_lib.Oracle(util.params_of(case), case.particles, nthreads=4)
+    o.step(steps, True)
+    ids = o.ids
+    where = {int(i): k for k, i in enumerate(ids)}
+    pick = np.array([where[int(i)] for i in g["ids"]])
+    assert o.report()["n_rebuilds"] == int(g["n_rebuilds"])
+    assert o.report()["total_time"] == pytest.approx(float(g["total_time"]), rel=1e-13)
+    assert util.relerr(o.get("rho")[pick], g["rho"]) < 1e-12
+    assert util.relerr(o.get("vel")[pick], g["vel"]) < 1e-9
+    assert util.relerr(o.get("pos")[pick], g["pos"]) < 1e-13
+    assert float(o.get("rho").sum()) == pytest.approx(float(g["sum_rho"]), rel=1e-13)
