@@ -186,4 +186,8 @@ def test_gpu_matches_the_committed_oracle_outputs(name, mk):
     util.check(util.relerr(st["Density"][pick], g["rho"]), 1e-10)
     util.check(util.relerr(st["Velocity"][pick], g["vel"]), 1e-8)
     util.check(util.relerr(st["Position"][pick], g["pos"]), 1e-12)
-    util.check(util.relerr(st["Pressure"][pick], g["press"]), 1e-6)
+    # (the reference's Pressure array lags: it holds P(ρₙ₊½) of the last pass; the device table carries P(ρ) of
+    #  the state it returns, so compare with the Tait EOS of the frozen densities, src/SimulationEquations.jl:9-11)
+    prm = util.params_of(case)
+    p_ref = (prm.c0 * prm.c0 * prm.rho0 / 7.0) * ((g["rho"] / prm.rho0) ** 7 - 1.0)
+    util.check(util.relerr(st["Pressure"][pick], p_ref), 1e-7)
