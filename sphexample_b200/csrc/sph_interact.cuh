@@ -601,22 +601,35 @@ __global__ void __launch_bounds__(BT) k_list_build(const InteractArgs<T, D> g) {
         auto flush = [&](bool final) {
             const int cnt = (int)((waddr - waddr0) / (uint32_t)(BT * 2));
             const int nchunks = final ? ((cnt + 7) >> 3) : (cnt >> 3);
-            const int m = final ? cnt : nchunks * 8;   // entries that leave now
-            BankRotator rot;
-            auto in = [&](int k) -> unsigned { return (unsigned)slist[k * BT + tid]; };
-            auto tmp = [&](int p) -> unsigned short & { return slist2[p * BT + tid]; };
-            if (ORDER) rot.prepare(m, tid, in, tmp);
-            for (int c = 0; c < nchunks; ++c) {
-                unsigned e[8];
+            if constexpr (!ORDER) {
+                // (kept in exactly this form: the instruction stream validated on hardware in round 1)
+                for (int c = 0; c < nchunks; ++c) {
+                    unsigned e[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int k = c * 8 + u;
-                    e[u] = (k < m) ? (ORDER ? rot.pull(k, tmp) : in(k)) : (unsigned)total;
+                    for (int u = 0; u < 8; ++u) e[u] = (c * 8 + u < cnt) ? (unsigned)slist[(c * 8 + u) * BT + tid] : (unsigned)total;
+                    if (lcount + 8 <= lcap && valid)
+                        gl[(size_t)(lcount >> 3) * g.nl_stride] =
+                            make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+                    lcount += 8;
                 }
-                if (lcount + 8 <= lcap && valid)
-                    gl[(size_t)(lcount >> 3) * g.nl_stride] =
-                        make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
-                lcount += 8;
+            } else {
+                const int m = final ? cnt : nchunks * 8;   // entries that leave now
+                BankRotator rot;
+                auto in = [&](int k) -> unsigned { return (unsigned)slist[k * BT + tid]; };
+                auto tmp = [&](int p) -> unsigned short & { return slist2[p * BT + tid]; };
+                rot.prepare(m, tid, in, tmp);
+                for (int c = 0; c < nchunks; ++c) {
+                    unsigned e[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = c * 8 + u;
+                        e[u] = (k < m) ? rot.pull(k, tmp) : (unsigned)total;
+                    }
+                    if (lcount + 8 <= lcap && valid)
+                        gl[(size_t)(lcount >> 3) * g.nl_stride] =
+                            make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+                    lcount += 8;
+                }
             }
             const int rem = final ? 0 : (cnt & 7);
             for (int u = 0; u < rem; ++u) slist[u * BT + tid] = slist[(nchunks * 8 + u) * BT + tid];
