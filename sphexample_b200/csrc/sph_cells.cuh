@@ -399,14 +399,20 @@ __global__ void k_build_bricks(Ctl *ctl, GridInfo *grid, const int *__restrict__
             roff[q] = rowbase + (ds * nm + dm) * nx;
         }
         // two walks of the same deterministic sequence: count, reserve, write
-        int nb = 0;
-        walk_row_bricks<NR>(cell_start, rowbase, nx, roff, bt, wlimit, [&](int, int) { ++nb; });
-        int out = atomicAdd(&grid->nbricks, nb);
-        if (out + nb > brick_cap) {
-            atomicCAS(&ctl->error, 0, SPH_ERR_ECAPACITY);
-            continue;
+        int out = 0, nb = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) {
+                out = atomicAdd(&grid->nbricks, nb);
+                if (out + nb > brick_cap) {
+                    atomicCAS(&ctl->error, 0, SPH_ERR_ECAPACITY);
+                    break;
+                }
+            }
+            walk_row_bricks<NR>(cell_start, rowbase, nx, roff, bt, wlimit, [&](int t0, int t1) {
+                if (pass) bricks[out++] = Brick{t0, t1};
+                else ++nb;
+            });
         }
-        walk_row_bricks<NR>(cell_start, rowbase, nx, roff, bt, wlimit, [&](int t0, int t1) { bricks[out++] = Brick{t0, t1}; });
     }
 }
 
