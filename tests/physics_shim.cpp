@@ -171,3 +171,30 @@ extern "C" int shim_bank_rotate(const unsigned short *entries, int m, int q, uns
     for (int k = 0; k < m; ++k) out[k] = (unsigned short)rot.pull(k, [&](int p) -> unsigned short & { return tmp[p]; });
     return m;
 }
+
+// step-by-step variant of shim_control_trace for tests whose particle motion depends on the dt decided here
+struct ShimCtl { Ctl ctl; GridInfo grid; };
+extern "C" void *shim_ctl_new(double delta_x0) {
+    ShimCtl *s = new ShimCtl;
+    memset(s, 0, sizeof *s);
+    s->ctl.delta_x = delta_x0;
+    return s;
+}
+extern "C" void shim_ctl_free(void *p) { delete (ShimCtl *)p; }
+extern "C" void shim_ctl_head(void *p, double disp2, double visc, double acc2, double vel2, double h, double c0, double cfl,
+                              double skin, double motion_vmax, int pause, double *out) {
+    ShimCtl *s = (ShimCtl *)p;
+    s->ctl.red_disp2 = bits_of(disp2);
+    s->ctl.red_visc = bits_of(visc);
+    s->ctl.red_acc2 = bits_of(acc2);
+    s->ctl.red_vel2 = bits_of(vel2);
+    step_control<double>(&s->ctl, &s->grid, h, c0, cfl, skin, motion_vmax, pause);
+    out[0] = s->ctl.dt; out[1] = s->ctl.do_rebuild; out[2] = s->ctl.list_build; out[3] = s->ctl.list_mode[0];
+    out[4] = s->ctl.list_mode[1]; out[5] = s->ctl.done; out[6] = s->ctl.list_move; out[7] = s->ctl.delta_x;
+}
+extern "C" void shim_ctl_body(void *p) {
+    ShimCtl *s = (ShimCtl *)p;
+    if (s->ctl.done && s->ctl.do_rebuild) s->ctl.done = 0;
+    s->ctl.do_rebuild = 0;
+    step_end(&s->ctl);
+}

@@ -112,3 +112,54 @@ def test_moving_bodies_count_towards_the_bound(shim):  # noqa: F811
     t0 = trace(shim, np.zeros(n), np.zeros(n), np.ones(n), np.zeros(n), skin=0.2 * H)
     t1 = trace(shim, np.zeros(n), np.zeros(n), np.ones(n), np.zeros(n), skin=0.2 * H, motion_vmax=2.8)
     assert t0["list_build"].sum() == 1 and t1["list_build"].sum() > 3
+
+
+def test_list_bound_holds_for_actual_symplectic_motion(shim):  # noqa: F811
+    """End-to-end check of the skin logic against real particle motion: particles move by the loop's
+    own update formulas (x½ = x + v·dt/2, v' = v + a·dt, x' = x + (v + v')/2·dt) under a random,
+    time-varying acceleration field, with dt, rebuilds and list decisions taken by the product's
+    step_control.  Whenever a pass is allowed to use the lists, every pair within H at that pass's
+    positions must already be in the list built (within H + skin) at the last build."""
+    rng = np.random.default_rng(4)
+    n, Hc, skin = 300, 2 * H, 0.1 * 2 * H
+    box = 6 * Hc
+    x = rng.uniform(0, box, (n, 3))
+    v = rng.normal(0, 2.0, (n, 3))
+    shim.shim_ctl_new.restype = C.c_void_p
+    shim.shim_ctl_new.argtypes = [C.c_double]
+    shim.shim_ctl_head.argtypes = [C.c_void_p] + [C.c_double] * 9 + [C.c_int, C.c_void_p]
+    shim.shim_ctl_body.argtypes = [C.c_void_p]
+    shim.shim_ctl_free.argtypes = [C.c_void_p]
+    ctl = shim.shim_ctl_new(1.0 + H)
+    out = np.zeros(8)
+
+    def within(p, r):
+        d2 = ((p[:, None, :] - p[None, :, :]) ** 2).sum(-1)
+        return d2 <= r * r
+
+    listed, x_half_prev, uses, builds = None, None, 0, 0
+    try:
+        for step in range(260):
+            a = rng.normal(0, 3.0e3, (n, 3)) * (1.0 + np.sin(0.05 * step))       # strong, varying accelerations
+            disp2 = 0.0 if x_half_prev is None else float(((x_half_prev - x) ** 2).sum(1).max())
+            shim.shim_ctl_head(ctl, disp2, 0.0, float((a ** 2).sum(1).max()), float((v ** 2).sum(1).max()), H, C0, CFL, skin, 0.0, 0,
+                               out.ctypes.data)
+            dt, build, m0, m1 = out[0], int(out[2]), int(out[3]), int(out[4])
+            if build:
+                listed = within(x, Hc + skin)                                      # k_list_build at xₙ
+                builds += 1
+            if m0 == 2:
+                assert listed is not None and not np.any(within(x, Hc) & ~listed), f"pass 1 of step {step}"
+                uses += 1
+            x_half = x + v * (dt / 2)
+            if m1 == 2:
+                assert not np.any(within(x_half, Hc) & ~listed), f"pass 2 of step {step}"
+                uses += 1
+            v_new = v + a * dt
+            x = x + (v + v_new) / 2 * dt
+            v = v_new
+            x_half_prev = x_half                                                   # xₙ⁺ of this step, compared with xₙ₊₁ at the next head
+            shim.shim_ctl_body(ctl)
+    finally:
+        shim.shim_ctl_free(ctl)
+    assert builds >= 3 and uses > 2 * builds                                       # the lists were reused, and rebuilt as particles moved
