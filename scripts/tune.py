@@ -17,8 +17,7 @@ from sphexample_b200.simulation import Simulation  # noqa: E402
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000
 t_prep = float(sys.argv[2]) if len(sys.argv) > 2 else 0.15
 steps = int(os.environ.get("SPH_STEPS", "120"))
-dflt = ("lists=1;lists=1,list_order=1;lists=1,skin=0.07;lists=1,skin=0.15;lists=1,list_order=1,skin=0.07;"
-        "lists=1,list_smem_kb=56;lists=1,list_smem_kb=100;lists=0")
+dflt = ("lists=1;lists=1,list_reorder=0;lists=1,skin=0.07;lists=1,skin=0.15;lists=0")
 sets = os.environ.get("SPH_SWEEP", dflt).split(";")
 case, dp = bench.build_case(n, "float32")
 p = bench.params_of(case)
@@ -54,5 +53,6 @@ for s in sets:
     r1 = sim.report()
     print(json.dumps({"opts": opts, "n": len(ids), "t_prep": t_prep, "vmax": round(vmax, 3), "ms_per_step": round(ms, 4),
                       "Mpu_s": round(len(ids) / ms / 1e3, 1), "list_builds": sim.stat("list_builds") - b0,
-                      "cell_rebuilds": r1["n_rebuilds"] - r0["n_rebuilds"], "steps": steps, "list_off": sim.stat("list_off")}), flush=True)
+                      "cell_rebuilds": r1["n_rebuilds"] - r0["n_rebuilds"], "steps": steps, "list_off": sim.stat("list_off"),
+                      "list_wavefronts": round(sim.stat("list_wavefronts"), 3), "list_entries": round(sim.stat("list_entries"), 1)}), flush=True)
     sim.close()

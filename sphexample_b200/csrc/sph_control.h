@@ -36,7 +36,7 @@ struct Ctl {
     unsigned long long red_vel2;  // max |v|² (bounds the displacement the neighbour lists have to absorb)
     // work distribution of the interaction kernel
     int bnd_done[2];           // slab mode: boundary-layer bricks finished in pass 1 / pass 2 of this step
-    int work_counter[8];       // [pass * 3 + part] (part 0 all / 1 boundary / 2 interior bricks); [6]: the list build
+    int work_counter[8];       // [pass * 3 + part] (part 0 all / 1 boundary / 2 interior bricks); [6]: the list build; [7]: the list reorder
     // per-particle neighbour lists (sph_interact.cuh): which kernel serves each pass of this step
     int list_mode[2];          // LM_CULL / LM_USE
     int list_build;            // this step starts with a list build (k_list_build)

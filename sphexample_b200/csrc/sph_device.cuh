@@ -96,6 +96,9 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     uint32_t addr = smem_u32(bar);
@@ -115,6 +118,14 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
                      smem_u32(smem_dst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// streaming 16-byte load through the read-only path, pinned where it is written (volatile): the
+// neighbour lists are read once per pass and never written while a pass runs
+__device__ __forceinline__ uint4 ld_nc_v4(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
 }
 
 template <class T> __device__ __forceinline__ T warp_max(T v) {

@@ -15,11 +15,13 @@
 //                    (~18 % hit rate in 3D) and runs the pair body in place, or (COMPACT) from
 //                    per-thread lists in shared memory so that the body executes on dense warps.
 //   k_list_build     the same walk without physics: records, per particle, every candidate inside
-//                    the window and within H + skin as (window index | role) in global memory.
-//   k_interact_list  stages the brick's whole window and runs the pair body over the recorded
-//                    entries only (~190 instead of ~770 candidates), branch-free.
+//                    the window and within H + skin as (window index | role) in global memory;
+//   k_list_reorder   gives every list the bank-aware entry order of sph_listorder.h;
+//   k_interact_ring  stages whole brick windows through a ring of shared-memory slots and runs the
+//                    pair body over the recorded entries only (~190 instead of ~770 candidates),
+//                    branch-free (these three live in sph_ring.cuh).
 //
-// ctl->list_mode[pass] (k_step_control) says which of k_interact / k_interact_list serves a pass;
+// ctl->list_mode[pass] (k_step_control) says which of k_interact / k_interact_ring serves a pass;
 // the other one returns at once.
 //
 // Pair-set fidelity: a candidate b is evaluated for target a iff b's (stale) cell is within the
@@ -86,7 +88,9 @@ struct InteractArgs {
     int *nl_cnt;
     size_t nl_stride;
     int lcap;                          // list capacity per particle (multiple of 8)
-    int list_cap_cand;                 // candidates the list kernel can stage per brick
+    int list_cap_cand;                 // candidates (incl. the 8 sentinel records) one ring slot of the list kernel holds
+    int *brick_total8;                 // per brick: window length rounded up to 8 = index of the first sentinel record
+    int list_reorder;                  // 1: k_list_reorder runs after a build (bank-aware entry order, sph_listorder.h)
     T Hs2;                             // (H + skin)^2: acceptance radius of a list build
     int force_cull;                    // 1: ignore ctl->list_mode (stage-level entry points)
 };
@@ -301,6 +305,8 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
 #pragma unroll
         for (int k = 0; k < D; ++k) acc[k] = T(0);
         const FastTarget<T> ft = make_fast_target<T>(ph, rho_a, P_a, rhon_a, ml_a, PASS == 0);   // !GENERIC only
+        FastSums<T, D> fs;
+        fast_zero(fs);
 
         // pair body for one staged candidate (smem slot sj), shared by both phases
         auto pair_body = [&](int sj, bool a_is_i) {
@@ -316,7 +322,7 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
                 r2 += xab[k] * xab[k];
             }
             if (!GENERIC) {
-                pair_fast<T, D, PASS == 0>(ph, ft, xab, r2, va, vb, rho_b, P_b, rhon_b, rsb > T(0), a_is_i, drho, acc);
+                pair_fast<T, D, PASS == 0>(ph, ft, xab, r2, va, vb, rho_b, P_b, rhon_b, rsb > T(0), a_is_i, fs);
             } else {
                 PairSide<T, D> sb;
 #pragma unroll
@@ -491,488 +497,9 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
         }
 
         // ---- epilogue ---------------------------------------------------------------------
+        if (!GENERIC) fast_finish<T, D>(ft, fs, drho, acc);
         if (valid) interact_epilogue<T, D, PASS, GENERIC>(g, i, xa, va, rho_a, sacc, drho, acc);
         __syncthreads();   // s_brick / s_off reuse
-        signal_boundary_brick(g, bidx, PASS);
-    }
-}
-
-// =================================================================================================
-// List build: the cull walk of k_interact without any physics.  Stages POSITIONS only, applies the
-// reference's stale-cell window test and r² <= (H + skin)², and appends (window index | role) to
-// the particle's list in global memory.  Runs when k_step_control raises ctl->list_build, on the
-// state-n positions, before pass 1 of that step.
-// =================================================================================================
-template <class T, int D, bool GENERIC, int BT, bool ORDER = false>
-__global__ void __launch_bounds__(BT) k_list_build(const InteractArgs<T, D> g) {
-    using L = Lay<T, D>;
-    using TA = typename L::TA;
-    constexpr int NR = (D == 3) ? 9 : 3;
-    constexpr int esA = sizeof(TA);
-
-    if (g.ctl->error || g.ctl->done || !g.ctl->list_build) return;
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int cap = g.cap;
-    TA *sA = reinterpret_cast<TA *>(smem_raw);
-    // per-thread append buffer slist[k * BT + tid] (LIST_CAP entries): accepted candidates are
-    // appended branch-free and leave for global memory 8 at a time as 16-byte stores
-    unsigned short *slist = reinterpret_cast<unsigned short *>(smem_raw + (size_t)cap * esA);
-    unsigned short *slist2 = slist + LIST_CAP * BT;   // scratch column of the bank-aware ordering (list_order only)
-
-    __shared__ uint64_t s_bar;
-    __shared__ int s_brick;
-    __shared__ int s_w0a[NR], s_len[NR], s_off[NR + 1];
-
-    const int tid = threadIdx.x;
-    const Phys<T> &ph = g.phys;
-    (void)ph;
-    if (tid == 0) {
-        mbar_init(&s_bar, 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    uint32_t phase = 0;
-
-    const int nx = g.grid->nx, nm = g.grid->nm;
-    const int nbricks = g.grid->nbricks;
-    const int npad = (g.grid->n_total + 3) & ~3;
-    const T Hs2 = g.Hs2;
-
-    for (;;) {
-        if (tid == 0) s_brick = atomicAdd(&g.ctl->work_counter[6], 1);
-        __syncthreads();
-        const int bidx = s_brick;
-        if (bidx >= nbricks) break;
-        const Brick br = g.bricks[bidx];
-        const int key0 = g.ckey[br.t0], key1 = g.ckey[br.t1 - 1];
-        const int cx0 = key0 % nx, cx1 = key1 % nx;
-        const int rowbase = key0 - cx0;
-        if (tid < NR) {
-            int dm = (D == 3) ? (tid % 3 - 1) : 0;
-            int ds = (D == 3) ? (tid / 3 - 1) : (tid - 1);
-            int rk = rowbase + (ds * nm + dm) * nx;
-            int w0 = g.cell_start[rk + cx0 - 1];
-            int w1 = g.cell_start[rk + cx1 + 2];
-            int w0a = w0 & ~3;
-            int w1a = min((w1 + 3) & ~3, npad);
-            if (w1 <= w0) w1a = w0a;
-            s_w0a[tid] = w0a;
-            s_len[tid] = w1a - w0a;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int o = 0;
-#pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                s_off[r] = o;
-                o += s_len[r];
-            }
-            s_off[NR] = o;
-            if (o + 1 > g.list_cap_cand || o >= LIST_IDX_MASK) atomicOr(&g.ctl->list_fail, 1);
-        }
-        __syncthreads();
-        const int total = s_off[NR];
-
-        const int i = br.t0 + tid;
-        const bool valid = i < br.t1;
-        const int warp_first = br.t0 + (tid & ~31);
-        const bool warp_has_work = warp_first < br.t1;
-        const int last_lane = min(31, br.t1 - warp_first - 1) & 31;
-        T xa[D];
-        int cxi = cx0, cs_a = 0, ce_a = 0;
-#pragma unroll
-        for (int k = 0; k < D; ++k) xa[k] = T(0);
-        if (valid) {
-            L::pos(g.A[i], xa);
-            int ki = g.ckey[i];
-            cxi = ki - rowbase;
-            cs_a = g.cell_start[ki];
-            ce_a = g.cell_start[ki + 1];
-        }
-        int lcount = 0;                       // list slots already in global memory (multiple of 8)
-        uint4 *const gl = g.nl + i;
-        const int lcap = g.lcap;
-        const uint32_t waddr0 = smem_u32(slist + tid);
-        const uint32_t waddr_full = waddr0 + (uint32_t)((LIST_CAP - 4) * BT * 2);   // > : fewer than 4 free
-        uint32_t waddr = waddr0;
-        // move whole chunks of 8 buffered entries to the global list; `final` pads the tail with the
-        // sentinel (window index `total`), otherwise up to 7 entries stay buffered
-        auto flush = [&](bool final) {
-            const int cnt = (int)((waddr - waddr0) / (uint32_t)(BT * 2));
-            const int nchunks = final ? ((cnt + 7) >> 3) : (cnt >> 3);
-            if constexpr (!ORDER) {
-                // (kept in exactly this form: the instruction stream validated on hardware in round 1)
-                for (int c = 0; c < nchunks; ++c) {
-                    unsigned e[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) e[u] = (c * 8 + u < cnt) ? (unsigned)slist[(c * 8 + u) * BT + tid] : (unsigned)total;
-                    if (lcount + 8 <= lcap && valid)
-                        gl[(size_t)(lcount >> 3) * g.nl_stride] =
-                            make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
-                    lcount += 8;
-                }
-            } else {
-                const int m = final ? cnt : nchunks * 8;   // entries that leave now
-                BankRotator rot;
-                auto in = [&](int k) -> unsigned { return (unsigned)slist[k * BT + tid]; };
-                auto tmp = [&](int p) -> unsigned short & { return slist2[p * BT + tid]; };
-                rot.prepare(m, tid, in, tmp);
-                for (int c = 0; c < nchunks; ++c) {
-                    unsigned e[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int k = c * 8 + u;
-                        e[u] = (k < m) ? rot.pull(k, tmp) : (unsigned)total;
-                    }
-                    if (lcount + 8 <= lcap && valid)
-                        gl[(size_t)(lcount >> 3) * g.nl_stride] =
-                            make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
-                    lcount += 8;
-                }
-            }
-            const int rem = final ? 0 : (cnt & 7);
-            for (int u = 0; u < rem; ++u) slist[u * BT + tid] = slist[(nchunks * 8 + u) * BT + tid];
-            waddr = waddr0 + (uint32_t)(rem * BT * 2);
-        };
-
-        for (int s0 = 0; s0 < total; s0 += cap) {
-            const int s1 = min(s0 + cap, total);
-            if (tid == 0) {
-                uint32_t bytes = 0;
-#pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                    int lo = max(s_off[r], s0), hi = min(s_off[r + 1], s1);
-                    if (lo < hi) bytes += (uint32_t)(hi - lo) * (uint32_t)esA;
-                }
-                fence_proxy_async();
-                mbar_arrive_expect_tx(&s_bar, bytes);
-#pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                    int lo = max(s_off[r], s0), hi = min(s_off[r + 1], s1);
-                    if (lo < hi)
-                        tma_load_1d(sA + (lo - s0), g.A + ((size_t)s_w0a[r] + (size_t)(lo - s_off[r])), (uint32_t)(hi - lo) * esA, &s_bar);
-                }
-            }
-            mbar_wait(&s_bar, phase);
-            phase ^= 1u;
-
-            for (int r = 0; r < NR; ++r) {
-                const int lo_s = max(s_off[r], s0), hi_s = min(s_off[r + 1], s1);
-                if (lo_s >= hi_s) continue;
-                const int dm = (D == 3) ? (r % 3 - 1) : 0;
-                const int ds = (D == 3) ? (r / 3 - 1) : (r - 1);
-                const int rk = rowbase + (ds * nm + dm) * nx;
-                int lo = 0, hi = 0;
-                if (valid) {
-                    lo = g.cell_start[rk + cxi - 1];
-                    hi = g.cell_start[rk + cxi + 2];
-                }
-                int major = g.ref_major_is_s ? ds : dm;
-                int minor = g.ref_major_is_s ? dm : ds;
-                int rowrole = major != 0 ? -major : -minor;
-                const int jbase = s_w0a[r] - s_off[r];       // global j = window index + jbase
-                int jb = lo_s + jbase, je = hi_s + jbase;
-                int ulo = __shfl_sync(0xffffffffu, lo, 0);
-                int uhi = __shfl_sync(0xffffffffu, hi, last_lane);
-                if (!warp_has_work) {
-                    ulo = INT_MAX;
-                    uhi = INT_MIN;
-                }
-                jb = max(jb, ulo) & ~3;
-                je = (min(je, uhi) + 3) & ~3;
-                const int sbase = -jbase - s0;               // smem slot = j + sbase
-                const unsigned wlen = (unsigned)(hi - lo);
-                const unsigned role_const = rowrole > 0 ? (unsigned)ROLE_BIT : 0u;
-                const unsigned self_off = (unsigned)(i - cs_a);
-                const bool same_row = rowrole == 0;
-                for (int j4 = jb; j4 < je; j4 += 4) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int j = j4 + u;
-                        T xb[D];
-                        L::pos(sA[j + sbase], xb);
-                        T r2 = T(0);
-#pragma unroll
-                        for (int k = 0; k < D; ++k) {
-                            T dlt = xa[k] - xb[k];
-                            r2 += dlt * dlt;
-                        }
-                        bool ok = (r2 <= Hs2) & ((unsigned)(j - lo) < wlen);
-                        if (GENERIC) ok &= (j != i);
-                        unsigned code = (unsigned)(j + (int)(role_const - (unsigned)jbase));
-                        if (same_row)
-                            code = (unsigned)(j - jbase) | (((j < ce_a) & ((unsigned)(j - cs_a) > self_off)) ? (unsigned)ROLE_BIT : 0u);
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\t"
-                            "setp.ne.u32 p, %2, 0;\n\t"
-                            "@p st.shared.u16 [%0], %1;\n\t"
-                            "@p add.u32 %0, %0, %3;\n\t}"
-                            : "+r"(waddr)
-                            : "h"((unsigned short)code), "r"((unsigned)ok), "n"(BT * 2)
-                            : "memory");
-                    }
-                    if (__any_sync(0xffffffffu, waddr > waddr_full)) flush(false);
-                }
-            }
-            __syncthreads();   // everyone is done with this stage's shared memory
-        }
-        flush(true);
-        if (valid) {
-            if (lcount > lcap) {
-                atomicOr(&g.ctl->list_fail, 2);
-                lcount = lcap;
-            }
-            g.nl_cnt[i] = lcount;   // slots incl. the sentinel padding of the last chunk
-        }
-        __syncthreads();   // s_brick / s_off reuse
-    }
-}
-
-// =================================================================================================
-// The LIST kernel.  Between two list builds the accepted neighbours of a particle barely change,
-// so re-testing the ~770 (3D) stencil candidates in every pass is wasted issue slots.  A build
-// (k_list_build) records, per particle, the window indices of all candidates that
-// pass the reference's stale-cell window test and lie within H + skin; until some pair could have
-// closed a gap of `skin` (k_step_control keeps the bound: 2 x accumulated max displacement), this
-// kernel evaluates the pair body over those ~180 entries only, ~75 % of which are inside H.
-//   * the brick's whole candidate window is staged into shared memory by the same TMA spans as in
-//     the cull kernel, so a list entry is a 15-bit window index + the role bit;
-//   * list chunks of 8 entries are 16-byte loads, coalesced across the warp ([chunk][particle]);
-//   * the accepted set is exactly the cull kernel's: r² <= H² is re-tested on current positions,
-//     and the window test was applied at build time (cells do not change between rebuilds).
-// =================================================================================================
-template <class T, int D, int PASS, bool GENERIC, int BT>
-__global__ void __launch_bounds__(BT) k_interact_list(const InteractArgs<T, D> g) {
-    using L = Lay<T, D>;
-    using TA = typename L::TA;
-    using TB = typename L::TB;
-    constexpr int NR = (D == 3) ? 9 : 3;
-    using SS = StageSizes<T, D, PASS, GENERIC>;
-
-    if (g.ctl->error || g.ctl->done) return;
-    if (g.ctl->list_mode[PASS] != LM_USE || g.ctl->list_fail) return;
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int cap = g.list_cap_cand;
-    TA *sA = reinterpret_cast<TA *>(smem_raw);
-    TB *sB = reinterpret_cast<TB *>(smem_raw + (size_t)cap * SS::esA);
-    T *sR = reinterpret_cast<T *>(smem_raw + (size_t)cap * (SS::esA + SS::esB));
-    TB *sBn = reinterpret_cast<TB *>(smem_raw + (size_t)cap * (SS::esA + SS::esB + SS::esR));
-
-    __shared__ uint64_t s_bar;
-    __shared__ int s_brick;
-    __shared__ int s_w0a[NR], s_len[NR], s_off[NR + 1];
-
-    const int tid = threadIdx.x;
-    const Phys<T> &ph = g.phys;
-    const bool use_sps = GENERIC && PASS && (ph.viscosity == V_SPS);
-
-    if (tid == 0) {
-        mbar_init(&s_bar, 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    uint32_t phase = 0;
-
-    const int nx = g.grid->nx, nm = g.grid->nm;
-    const int nbricks = g.grid->nbricks;
-    const int brick_first = g.brick_part == 2 ? g.grid->nbricks_bnd : 0;
-    const int brick_end = g.brick_part == 1 ? g.grid->nbricks_bnd : nbricks;
-    const int npad = (g.grid->n_total + 3) & ~3;
-
-    for (;;) {
-        if (tid == 0) s_brick = brick_first + atomicAdd(&g.ctl->work_counter[g.counter_slot], 1);
-        __syncthreads();
-        const int bidx = s_brick;
-        if (bidx >= brick_end) break;
-        const Brick br = g.bricks[bidx];
-        const int key0 = g.ckey[br.t0], key1 = g.ckey[br.t1 - 1];
-        const int cx0 = key0 % nx, cx1 = key1 % nx;
-        const int rowbase = key0 - cx0;
-        // candidate spans: identical arithmetic to the cull kernel (the list indexes this window)
-        if (tid < NR) {
-            int dm = (D == 3) ? (tid % 3 - 1) : 0;
-            int ds = (D == 3) ? (tid / 3 - 1) : (tid - 1);
-            int rk = rowbase + (ds * nm + dm) * nx;
-            int w0 = g.cell_start[rk + cx0 - 1];
-            int w1 = g.cell_start[rk + cx1 + 2];
-            int w0a = w0 & ~3;
-            int w1a = min((w1 + 3) & ~3, npad);
-            if (w1 <= w0) w1a = w0a;
-            s_w0a[tid] = w0a;
-            s_len[tid] = w1a - w0a;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int o = 0;
-#pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                s_off[r] = o;
-                o += s_len[r];
-            }
-            s_off[NR] = o;
-            // stage the whole window
-            uint32_t bytes = (uint32_t)o * (uint32_t)(SS::per_candidate - (use_sps ? 0 : SS::esBn));
-            if (bytes) {
-                fence_proxy_async();
-                mbar_arrive_expect_tx(&s_bar, bytes);
-#pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                    const int len = s_len[r];
-                    if (len > 0) {
-                        const size_t src = (size_t)s_w0a[r];
-                        const int dst = s_off[r];
-                        tma_load_1d(sA + dst, g.A + src, (uint32_t)len * SS::esA, &s_bar);
-                        tma_load_1d(sB + dst, g.B + src, (uint32_t)len * SS::esB, &s_bar);
-                        if (PASS) tma_load_1d(sR + dst, g.RN + src, (uint32_t)len * SS::esR, &s_bar);
-                        if (use_sps) tma_load_1d(sBn + dst, g.Bn + src, (uint32_t)len * SS::esBn, &s_bar);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        const int total = s_off[NR];
-
-        // ---- this thread's target particle (overlaps the TMA flight) -----------------------
-        const int i = br.t0 + tid;
-        const bool valid = i < br.t1;
-        T xa[D], va[D], rho_a = T(1), P_a = T(0), rhon_a = T(1), ml_a = T(0);
-#pragma unroll
-        for (int k = 0; k < D; ++k) xa[k] = va[k] = T(0);
-        int nchunk = 0;
-        if (valid) {
-            T rs;
-            L::unpack(g.A[i], g.B[i], xa, va, rs, P_a);
-            rho_a = sph_abs(rs);
-            ml_a = rs > T(0) ? T(1) : T(0);
-            rhon_a = PASS ? g.RN[i] : rho_a;
-            nchunk = (g.nl_cnt[i] + 7) >> 3;
-        }
-        const uint4 *lp = g.nl + i;
-        uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (nchunk > 0) nxt = lp[0];
-        PairSide<T, D> sa;
-        PairAccum<T, D> sacc;
-        accum_zero(sacc);
-        if (GENERIC) {
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                sa.x[k] = xa[k];
-                sa.v[k] = va[k];
-                sa.vn[k] = va[k];
-            }
-            sa.rho = rho_a;
-            sa.P = P_a;
-            sa.rho_n = rhon_a;
-            sa.ml = ml_a;
-            if (use_sps && valid) {
-                T dummy_x[D], rs, Pd;
-                L::unpack(g.An_rw[i], g.Bn_rw[i], dummy_x, sa.vn, rs, Pd);
-            }
-        }
-        T drho = T(0), acc[D];
-#pragma unroll
-        for (int k = 0; k < D; ++k) acc[k] = T(0);
-        const FastTarget<T> ft = make_fast_target<T>(ph, rho_a, P_a, rhon_a, ml_a, PASS == 0);
-
-        if (total > 0) {
-            mbar_wait(&s_bar, phase);
-            phase ^= 1u;
-        }
-        // sentinel candidate (window index `total`): infinitely far away, so r² <= H² fails
-        if (tid == 0) {
-            T far[D], zero[D];
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                far[k] = T(1e15);   // finite: the masked pair body must not meet inf * 0
-                zero[k] = T(0);
-            }
-            TA fa;
-            TB fb;
-            L::pack(fa, fb, far, zero, T(1), T(0));
-            sA[total] = fa;
-            sB[total] = fb;
-            if (PASS) sR[total] = T(1);
-        }
-        __syncthreads();
-
-        const T H2 = ph.H2;
-        auto pair_entry = [&](unsigned e) {
-            const int sj = (int)(e & LIST_IDX_MASK);
-            const bool a_is_i = (e >> 15) != 0;
-            T xb[D], vb[D], rsb, P_b;
-            L::unpack(sA[sj], sB[sj], xb, vb, rsb, P_b);
-            T xab[D], r2 = T(0);
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                xab[k] = xa[k] - xb[k];
-                r2 += xab[k] * xab[k];
-            }
-            T rho_b = sph_abs(rsb);
-            T rhon_b = PASS ? sR[sj] : rho_b;
-            if (!GENERIC) {
-                // branch-free: the 8 entries of a chunk interleave (the kernel is latency-bound at the
-                // occupancy its shared-memory window allows); entries outside H contribute exact zeros
-                pair_fast<T, D, PASS == 0, true>(ph, ft, xab, r2, va, vb, rho_b, P_b, rhon_b, rsb > T(0), a_is_i, drho, acc);
-            } else if (r2 <= H2) {
-                PairSide<T, D> sb;
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    sb.x[k] = xb[k];
-                    sb.v[k] = vb[k];
-                    sb.vn[k] = vb[k];
-                }
-                sb.rho = rho_b;
-                sb.P = P_b;
-                sb.rho_n = rhon_b;
-                sb.ml = rsb > T(0) ? T(1) : T(0);
-                if (use_sps) L::vel(sBn[sj], sb.vn);
-                pair_generic<T, D>(ph, sa, sb, xab, r2, a_is_i, sacc);
-            }
-        };
-        const int mchunk = warp_max(nchunk);
-        for (int c = 0; c < mchunk; ++c) {
-            const uint4 cur = nxt;
-            if (c + 1 < nchunk) nxt = lp[(size_t)(c + 1) * g.nl_stride];
-            if (c < nchunk) {
-                const unsigned e8[8] = {cur.x & 0xffffu, cur.x >> 16, cur.y & 0xffffu, cur.y >> 16,
-                                        cur.z & 0xffffu, cur.z >> 16, cur.w & 0xffffu, cur.w >> 16};
-                if (!GENERIC) {
-                    // all 16-24 shared-memory gathers of the chunk first, then the 8 masked pair
-                    // bodies: the loads' latency is paid once per chunk, not once per entry
-                    TA a8[8];
-                    TB b8[8];
-                    T r8[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int sj = (int)(e8[u] & LIST_IDX_MASK);
-                        a8[u] = sA[sj];
-                        b8[u] = sB[sj];
-                        if (PASS) r8[u] = sR[sj];
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        T xb[D], vb[D], rsb, P_b;
-                        L::unpack(a8[u], b8[u], xb, vb, rsb, P_b);
-                        T xab[D], r2 = T(0);
-#pragma unroll
-                        for (int k = 0; k < D; ++k) {
-                            xab[k] = xa[k] - xb[k];
-                            r2 += xab[k] * xab[k];
-                        }
-                        const T rho_b = sph_abs(rsb);
-                        pair_fast<T, D, PASS == 0, true>(ph, ft, xab, r2, va, vb, rho_b, P_b, PASS ? r8[u] : rho_b, rsb > T(0),
-                                                         (e8[u] >> 15) != 0, drho, acc);
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) pair_entry(e8[u]);
-                }
-            }
-        }
-        if (valid) interact_epilogue<T, D, PASS, GENERIC>(g, i, xa, va, rho_a, sacc, drho, acc);
-        __syncthreads();   // shared window / s_brick reuse
         signal_boundary_brick(g, bidx, PASS);
     }
 }

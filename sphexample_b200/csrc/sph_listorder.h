@@ -1,14 +1,19 @@
-// sph_listorder.h — bank-aware ordering of neighbour-list entries (host + device, shared with the
-// CPU tests through tests/physics_shim.cpp).
+// sph_listorder.h — bank-aware ("rainbow") ordering of one particle's neighbour list (host + device;
+// the CPU tests drive this very code through tests/physics_shim.cpp).
 //
 // The list kernel gathers one 16-byte candidate record per lane and list position with LDS.128.
 // The 8 lanes of a quarter warp are served together; two lanes that want DIFFERENT records in the
 // same 16-byte bank group (record index mod 8) cost an extra wavefront.  With lists in window order
-// the indices are effectively random: 3.1 wavefronts per quarter-warp load measured on B200
-// (profiles/r1m), 2.5 in the CPU model (scripts/sim_list_conflicts.py).  The order of the entries
-// inside a particle's list is free (it only changes the summation order), so the build can hand
-// lane q (= lane & 7) an order whose k-th entry lies in bank group (q + k) mod 8 whenever it still
-// has one: the 8 lanes then hit 8 different groups.  CPU model: 1.3 wavefronts per load.
+// the indices are effectively random: 9.3 wavefronts per warp-wide LDS.128 in the CPU model
+// (scripts/sim_list_conflicts.py), 12.5 measured on B200 (profiles/r1m) — the list kernel was bound
+// by exactly that.  The order of the entries inside a particle's list is free (it only changes the
+// summation order), so lane q (= particle index in its brick, mod 8) stores its list as "rainbow"
+// chunks of 8: slot u of EVERY chunk holds an entry of bank group (q + u) mod 8.  At any list
+// position the 8 lanes of a quarter warp then read 8 different bank groups: conflict-free.
+// A particle's entries are not spread evenly over the 8 groups; entries of an over-full group
+// (more than the list has chunks) go into the holes the under-full groups leave, and what holes
+// remain are padded with the sentinel of THEIR group (8 sentinel records, one per group, sit behind
+// the staged window).  CPU model of the result: 4.4 wavefronts per LDS.128 (4 is the floor).
 #pragma once
 
 #if defined(__CUDACC__)
@@ -19,54 +24,46 @@
 
 namespace sph {
 
-// Reorders a batch of m <= 64 entries.  `in(k)` reads entry k of the batch (window order),
-// `tmp(p)` is a reference to scratch slot p (m slots).  After prepare(), pull(k) returns the entry
-// for position k = 0 .. m-1 of the batch, each entry exactly once.
-struct BankRotator {
-    unsigned long long next, rem;   // 8 x 8-bit: next scratch slot / entries left, per bank group
-    int q;
+constexpr unsigned LIST_INDEX_MASK = 0x7fffu;   // entry = window index | role << 15
 
-    template <class In, class Tmp>
-    SPH_LO_HD void prepare(int m, int lane_q, In in, Tmp tmp) {
-        q = lane_q & 7;
-        unsigned long long cnt = 0;
-        for (int k = 0; k < m; ++k) cnt += 1ull << (8 * (in(k) & 7u));
-        unsigned long long startp = 0;
-        unsigned acc = 0;
-        for (int r = 0; r < 8; ++r) {
-            startp |= (unsigned long long)acc << (8 * r);
-            acc += (unsigned)((cnt >> (8 * r)) & 0xffull);
+// One particle.  in(k), k < n_slots (a multiple of 8): the list as built, window order, padded with
+// entries whose index is >= total8.  out(c, u): slot u of chunk c of the reordered list
+// (n_slots / 8 chunks).  ovf(p), p < ovf_cap: scratch for the entries of over-full groups.
+// q: the particle's lane phase.  Returns false (and leaves `out` unusable) when the scratch is too
+// small — the caller then keeps the list as built, which is valid, only slower.
+template <class In, class Out, class Ovf>
+SPH_LO_HD bool rainbow_order(int n_slots, int q, unsigned total8, In in, Out out, Ovf ovf, int ovf_cap) {
+    const int nc = n_slots >> 3;
+    unsigned cnt_lo = 0u, cnt_hi = 0u;   // 8 x 8-bit entry counts per bank group (a list holds < 256 per group)
+    int novf = 0;
+    bool ok = true;
+    for (int k = 0; k < n_slots; ++k) {
+        const unsigned e = in(k);
+        const unsigned idx = e & LIST_INDEX_MASK;
+        if (idx >= total8) continue;   // padding of the build
+        const unsigned r = idx & 7u;
+        const unsigned sh = (r & 3u) * 8u;
+        const unsigned c = (((r & 4u) ? cnt_hi : cnt_lo) >> sh) & 0xffu;
+        if (r & 4u) cnt_hi += 1u << sh;
+        else cnt_lo += 1u << sh;
+        if ((int)c < nc) {
+            out((int)c, (int)((r - (unsigned)q) & 7u)) = (unsigned short)e;
+        } else if (novf < ovf_cap) {
+            ovf(novf++) = (unsigned short)e;
+        } else {
+            ok = false;
         }
-        unsigned long long fill = startp;
-        for (int k = 0; k < m; ++k) {            // stable bucket copy into the scratch column
-            const unsigned e = in(k);
-            const unsigned r = e & 7u;
-            tmp((int)((fill >> (8 * r)) & 0xffull)) = (unsigned short)e;
-            fill += 1ull << (8 * r);
-        }
-        next = startp;
-        rem = cnt;
     }
-
-    template <class Tmp>
-    SPH_LO_HD unsigned pull(int k, Tmp tmp) {
-        unsigned r = (unsigned)(q + k) & 7u;
-        if (((rem >> (8 * r)) & 0xffull) == 0) {   // that group is exhausted: take from the fullest one
-            unsigned best = 0, bc = 0;
-            for (unsigned r2 = 0; r2 < 8; ++r2) {
-                const unsigned c = (unsigned)((rem >> (8 * r2)) & 0xffull);
-                if (c > bc) {
-                    bc = c;
-                    best = r2;
-                }
-            }
-            r = best;
-        }
-        const int p = (int)((next >> (8 * r)) & 0xffull);
-        next += 1ull << (8 * r);
-        rem -= 1ull << (8 * r);
-        return (unsigned)tmp(p);
+    if (!ok) return false;
+    // holes: chunks [count of group r, nc) of slot (r - q) & 7; over-full groups' entries first, then
+    // the group's own sentinel (window index total8 + r: same bank group as the slot expects)
+    int po = 0;
+    for (unsigned r = 0; r < 8u; ++r) {
+        const unsigned c0 = (((r & 4u) ? cnt_hi : cnt_lo) >> ((r & 3u) * 8u)) & 0xffu;
+        const int u = (int)((r - (unsigned)q) & 7u);
+        for (int c = (int)c0; c < nc; ++c) out(c, u) = (po < novf) ? (unsigned short)ovf(po++) : (unsigned short)(total8 + r);
     }
-};
+    return true;
+}
 
 }  // namespace sph

@@ -149,65 +149,86 @@ SPH_HD void accum_zero(PairAccum<T, D> &s) {
 // FAST path: WendlandC2 + ArtificialViscosity + LinearDensityDiffusion, no shifting / kernel
 // output — the model set of every BASELINE config (example/Dambreak3d.jl:57-59 etc.).
 // xab / r2 are passed in because the caller has just computed them for the cut-off test.
+//
+// The reference's per-pair expressions (src/SPHCellList.jl:268-317) are regrouped so that every
+// factor that depends on the target particle only leaves the neighbour sum:
+//   dρ/dt|a = [αD 5/(8h²)] · ( ρ_a m0 · S1  −  2 δφ h c0 m0 ML_a · S2 )
+//   dv/dt|a = [αD 5/(8h²)] · (m0/ρ_a) · S3
+//     S1 = Σ_b (q−2)³ (1/ρ_b) v_ab·x_ab                                     continuity, :288-291
+//     S2 = Σ_b fluid_b (q−2)³ V_ab (ρₙ_b − ρₙ_a − ρᴴ_ab) r²/(r²+η²),   V_ab = 1/ρₙ of the "j" role (Q1, Q2)
+//     S3 = Σ_b (q−2)³ [ (2 α c0 h ρ_a/m0)… min(v_ab·x_ab,0) / ((r²+η²)(ρₙ_a+ρₙ_b)) − (P_a+P_b)/ρ_b ] x_ab
+// (∇W = αD 5 (q−2)³/(8h²) x_ab, src/SPHKernels.jl:80-87).  The two reciprocals 1/(r²+η²) and
+// 1/(ρₙ_a+ρₙ_b) come from ONE reciprocal of their product.  Per pair: sqrt, 1/ρ_b, that reciprocal
+// (+ 1/ρₙ_b in pass 2) — on the device in fp32 single MUFU approximations (1-2 ulp), IEEE in fp64
+// and on the host; see the tolerances in tests/test_gpu_parity.py.
 // ---------------------------------------------------------------------------------------------
-// Per-target constants of the fast pair body (computed once per particle, not per pair).
 template <class T>
 struct FastTarget {
-    T P, rhon, inv_rhon;   // P_a, ρₙ_a, 1/ρₙ_a
-    T c_cont;              //  ρ_a m0                    continuity prefactor
-    T c_ddt;               // −2 δφ h c0 m0 ML_a         diffusion prefactor
-    T c_pres;              // −m0 / ρ_a                  pressure prefactor
+    T P, rhon, inv_rhon;     // P_a, ρₙ_a, 1/ρₙ_a
+    T c_visc;                // 2 α c0 h ρ_a            (visc_k2 ρ_a / m0)
+    T k_cont, k_ddt, k_acc;  // scales applied once to S1, S2, S3 (fast_finish)
 };
+template <class T, int D>
+struct FastSums {
+    T s1, s2, s3[D];
+};
+template <class T, int D>
+SPH_HD void fast_zero(FastSums<T, D> &s) {
+    s.s1 = s.s2 = T(0);
+    for (int k = 0; k < D; ++k) s.s3[k] = T(0);
+}
 template <class T>
 SPH_HD FastTarget<T> make_fast_target(const Phys<T> &p, T rho, T P, T rhon, T ml, bool same_rho) {
     FastTarget<T> f;
     f.P = P;
     f.rhon = rhon;
-    T inv_rho = sph_rcp(rho);
-    f.inv_rhon = same_rho ? inv_rho : sph_rcp(rhon);
-    f.c_cont = rho * p.m0;
-    f.c_ddt = T(-2) * p.ddt_k * p.m0 * ml;
-    f.c_pres = -p.m0 * inv_rho;
+    T inv_rho = T(1) / rho;
+    f.inv_rhon = same_rho ? inv_rho : T(1) / rhon;
+    f.c_visc = (p.visc_k2 / p.m0) * rho;
+    f.k_cont = p.gradw_c * (rho * p.m0);
+    f.k_ddt = p.gradw_c * (T(-2) * p.ddt_k * p.m0 * ml);
+    f.k_acc = p.gradw_c * (p.m0 * inv_rho);
     return f;
+}
+template <class T, int D>
+SPH_HD void fast_finish(const FastTarget<T> &a, const FastSums<T, D> &s, T &drho, T *acc) {
+    drho = a.k_cont * s.s1 + a.k_ddt * s.s2;
+    for (int k = 0; k < D; ++k) acc[k] = a.k_acc * s.s3[k];
 }
 
 // SAME_RHO: the pass density is the state-n density (pass 1 of the step), so 1/ρ_b serves both
 // the continuity/pressure terms and the diffusion volume.
-// Divisions are restated as products with reciprocals (one per distinct denominator); on the
-// device the fp32 reciprocals and the square root are single MUFU approximations (1-2 ulp), the
-// fp64 ones stay IEEE divisions — see the tolerances in tests/test_gpu_parity.py.
-// MASKED: evaluate unconditionally and zero the kernel-gradient factor when r² > H² (every term
-// carries it), so that a caller can run several candidates back to back without branches.
-template <class T, int D, bool SAME_RHO, bool MASKED = false>
+// Branch-free: (q−2) is clamped at 0, so a candidate beyond the support (q >= 2, i.e. r² > H² up to
+// the rounding of sqrt) contributes exact zeros to every sum and callers may feed candidates
+// without testing r² <= H² first.  fp64 keeps the reference's exact acceptance test.
+template <class T, int D, bool SAME_RHO>
 SPH_HD void pair_fast(const Phys<T> &p, const FastTarget<T> &a, const T *xab, T r2, const T *va, const T *vb, T rho_b,
-                      T P_b, T rhon_b, bool fluid_b, bool a_is_i, T &drho, T *acc) {
-    // ∇W = fac * x_ab with fac = αD 5 (q−2)³ / (8h²), src/SPHKernels.jl:80-87.  q = clamp(d/h, 0, 2):
-    // the lower clamp is vacuous (d >= 0) and the upper one only guards the rounding of an accepted
-    // pair (r² <= H²); it is kept in fp64 and dropped in fp32 where (q−2)³ <= 1e-20 there.
+                      T P_b, T rhon_b, bool fluid_b, bool a_is_i, FastSums<T, D> &s) {
     T d = sph_sqrt_fast(r2);
-    T qm2 = (sizeof(T) == 8) ? sph_min(d * p.h_inv, T(2)) - T(2) : d * p.h_inv - T(2);
-    T fac = (p.gradw_c * qm2) * (qm2 * qm2);
-    if (MASKED) fac = (r2 <= p.H2) ? fac : T(0);
+    T qm2;
+    if (sizeof(T) == 8) {
+        qm2 = sph_min(d * p.h_inv, T(2)) - T(2);
+        qm2 = (r2 <= p.H2) ? qm2 : T(0);
+    } else {
+        qm2 = sph_min(d * p.h_inv - T(2), T(0));
+    }
+    T fac = qm2 * (qm2 * qm2);
     T vdotx = T(0);
 #pragma unroll
     for (int k = 0; k < D; ++k) vdotx += (va[k] - vb[k]) * xab[k];
     T inv_rho_b = sph_rcp(rho_b);
     T inv_rhon_b = SAME_RHO ? inv_rho_b : sph_rcp(rhon_b);
-    // continuity, src/SPHCellList.jl:288-291: dρ/dt|a += ρ_a (m0/ρ_b) v_ab·∇W
-    drho += (a.c_cont * inv_rho_b) * (fac * vdotx);
-    // Linear density diffusion, src/SPHDensityDiffusionModels.jl:113-135:
-    //   D = δφ h c0 (m0/ρ_role-j) 2(ρ_b − ρ_a − ρᴴ)(−x_ab·∇W)/(r²+η²) ML_a ML_b     (Q1, Q2)
-    T inv = sph_rcp(r2 + p.eta2);
+    s.s1 += (inv_rho_b * fac) * vdotx;
+    T sum_rhon = a.rhon + rhon_b;
+    T ip = sph_rcp((r2 + p.eta2) * sum_rhon);   // 1 / ((r²+η²)(ρₙ_a+ρₙ_b))
+    T inv = ip * sum_rhon;                      // 1 / (r²+η²)
     T diff = (rhon_b - a.rhon) - p.ddt_lin * xab[D - 1];
-    T dd = (a.c_ddt * (a_is_i ? inv_rhon_b : a.inv_rhon)) * (diff * ((fac * r2) * inv));
-    drho += fluid_b ? dd : T(0);
-    // momentum: pressure + artificial viscosity (only approaching pairs: min(v·x, 0)), :299-309,
-    // src/SPHViscosityModels.jl:56-74
-    T coef = (a.P + P_b) * (a.c_pres * inv_rho_b);
-    coef += (p.visc_k2 * (sph_min(vdotx, T(0)) * inv)) * sph_rcp(a.rhon + rhon_b);
-    T cf = coef * fac;
+    T dd = (a_is_i ? inv_rhon_b : a.inv_rhon) * (diff * ((fac * r2) * inv));
+    s.s2 += fluid_b ? dd : T(0);
+    T c1 = a.c_visc * (sph_min(vdotx, T(0)) * ip) - (a.P + P_b) * inv_rho_b;
+    T cf = c1 * fac;
 #pragma unroll
-    for (int k = 0; k < D; ++k) acc[k] += cf * xab[k];
+    for (int k = 0; k < D; ++k) s.s3[k] += cf * xab[k];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <chrono>
 #include <numeric>
 #include <thread>
@@ -23,6 +24,7 @@
 #include "../../include/sphb200.h"
 #include "sph_cells.cuh"
 #include "sph_interact.cuh"
+#include "sph_ring.cuh"
 #include "sph_slab.cuh"
 #include "sph_step.cuh"
 
@@ -186,8 +188,8 @@ class Sim final : public sphb200_sim {
     int64_t launches = 0;
     // options
     int opt_compact, opt_tma, opt_smem_kb, opt_batch;
-    int opt_lists, opt_lcap, opt_list_smem_kb;   // per-particle neighbour lists (sph_interact.cuh)
-    int opt_list_order;                          // bank-aware entry order (sph_listorder.h); off until validated on hardware
+    int opt_lists, opt_lcap, opt_list_smem_kb;   // per-particle neighbour lists (sph_ring.cuh)
+    int opt_list_reorder;                        // bank-aware entry order (sph_listorder.h, k_list_reorder)
     double opt_skin;                             // list skin as a fraction of H
     DevBuf<uint4> nl;
     DevBuf<int> nl_cnt;
@@ -212,6 +214,9 @@ class Sim final : public sphb200_sim {
     // cell structure
     DevBuf<int> cell_count, cell_start, scan_partial;
     DevBuf<Brick> bricks;
+    DevBuf<int> brick_total8;   // per brick: sentinel base of its candidate window (k_list_build -> k_list_reorder)
+    // cudaFuncSetAttribute / occupancy results are per device and per handle: kernel -> {dynamic smem, CTAs per SM}
+    std::map<const void *, std::pair<int, int>> kernel_cfg;
     long long cell_cap = 0, row_cap = 0;
     int brick_cap = 0;
     DevBuf<Ctl> d_ctl;
@@ -236,9 +241,9 @@ class Sim final : public sphb200_sim {
         // (2D fp64 windows fit too: C2 186 -> 325 Mpu/s, profiles/r1m_configs.jsonl)
         opt_lists = env_int("SPHB200_LISTS", (sizeof(T) == 4 || D == 2) ? 1 : 0);
         opt_lcap = env_int("SPHB200_LCAP", D == 3 ? 320 : 96);
-        opt_list_smem_kb = env_int("SPHB200_LIST_SMEM_KB", 72);   // 3 CTAs per SM (r1 sweep: 56 / 72 / 100 KB -> 0.81 / 0.69 / 0.80 ms per pass)
+        opt_list_smem_kb = env_int("SPHB200_LIST_SMEM_KB", 0);    // > 0: pretend a ring slot holds only this much (tests of the overflow fallback)
         opt_skin = env_int("SPHB200_SKIN_PCT", 10) * 0.01;
-        opt_list_order = env_int("SPHB200_LIST_ORDER", 0);
+        opt_list_reorder = env_int("SPHB200_LIST_REORDER", 1);
         am.ax_s = D - 1;   // default: the reference's most significant axis
         am.ax_m = (D == 3) ? 1 : 0;
         build_phys();
@@ -335,7 +340,7 @@ class Sim final : public sphb200_sim {
         else if (k == "skin") opt_skin = value;
         else if (k == "lcap") opt_lcap = std::max(8, ((int)value + 7) & ~7);
         else if (k == "list_smem_kb") opt_list_smem_kb = (int)value;
-        else if (k == "list_order") opt_list_order = (int)value;
+        else if (k == "list_reorder") opt_list_reorder = (int)value;
         else return fail(SPHB200_EINVAL, "unknown option '%s'", k.c_str());
         return SPHB200_OK;
     }
@@ -352,6 +357,20 @@ class Sim final : public sphb200_sim {
         else if (k == "halo_bytes_per_step") *value = (double)slab.halo_bytes_per_step;
         else if (k == "migrated") *value = (double)slab.n_migrated;
         else if (k == "n_total") *value = (double)n;
+        else if (k == "list_wavefronts" || k == "list_entries") {
+            // model cost of the lists in memory: wavefronts per quarter-warp 16-byte gather (1.0 = conflict-free)
+            if (!lists_on() || !h_ctl->list_valid) { *value = 0.0; return SPHB200_OK; }
+            DevBuf<unsigned long long> acc3;
+            CK(acc3.alloc(3));
+            CK(cudaMemsetAsync(acc3.p, 0, 24, stream));
+            k_list_diag<<<num_sms * 4, 128, 0, stream>>>(d_grid.p, bricks.p, brick_total8.p, nl.p, nl_cnt.p, nl_stride, acc3.p);
+            ++launches;
+            unsigned long long h3[3];
+            CK(cudaMemcpyAsync(h3, acc3.p, 24, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            *value = (k == "list_entries") ? (double)h3[2] / std::max<double>(1.0, (double)num_particles())
+                                           : (double)h3[0] / std::max<double>(1.0, (double)h3[1]);
+        }
         else return fail(SPHB200_EINVAL, "unknown stat '%s'", k.c_str());
         return SPHB200_OK;
     }
@@ -429,6 +448,7 @@ class Sim final : public sphb200_sim {
         row_cap = cap / 3 + 1;
         brick_cap = (int)std::min<long long>((long long)(n_alloc / 8) + row_cap + 16, INT_MAX);
         CK(bricks.alloc((size_t)brick_cap));
+        CK(brick_total8.alloc((size_t)brick_cap));
         return SPHB200_OK;
     }
 
@@ -716,13 +736,21 @@ class Sim final : public sphb200_sim {
     }
 
     bool lists_on() const { return opt_lists && !prm.shifting && opt_skin > 0.0; }
-    // candidates a brick's window may hold: what the list kernel can stage (pass 2 layout), else a
-    // bound that merely keeps sparse rows from producing row-long windows
+    // candidates one ring slot of the list kernel holds (sentinels included)
+    int list_cap_cand() const {
+        int cap = generic ? RingGeom<T, D, true>::CAP : RingGeom<T, D, false>::CAP;
+        if (opt_list_smem_kb > 0) {
+            const int per = generic ? RingGeom<T, D, true>::S1::per_candidate : RingGeom<T, D, false>::S1::per_candidate;
+            cap = std::min(cap, ((opt_list_smem_kb * 1024 - 64) / per) & ~7);
+        }
+        return cap;
+    }
+    // candidates a brick's window may hold: what the list kernel can stage, else a bound that merely
+    // keeps sparse rows from producing row-long windows
     int brick_window_limit() {
         if (!lists_on()) return 8192;
-        int smem, cap;
-        if (generic ? list_geometry<1, true>(&smem, &cap) : list_geometry<1, false>(&smem, &cap)) return 8192;
-        return cap - 64;   // room for the 4-element alignment of the 3^(D-1) spans and the sentinel
+        const int lim = list_cap_cand() - 16 - 6 * ((D == 3) ? 9 : 3);   // RingGeom::WINDOW_LIMIT for the effective cap
+        return lim >= 64 ? lim : 64;
     }
     double motion_vmax() const {
         double v = 0.0;
@@ -780,74 +808,76 @@ class Sim final : public sphb200_sim {
         g.nl_cnt = nl_cnt.p;
         g.nl_stride = nl_stride;
         g.lcap = opt_lcap;
+        g.list_cap_cand = list_cap_cand();
+        g.brick_total8 = brick_total8.p;
+        g.list_reorder = opt_list_reorder;
         const double Hs = prm.H * (1.0 + opt_skin);
         g.Hs2 = (T)(Hs * Hs);
         g.force_cull = cull_force;
     }
-    template <int PASS, bool GEN>
-    int list_geometry(int *smem_out, int *cap_out) {
-        using SS = StageSizes<T, D, PASS, GEN>;
-        int smem = std::min(opt_list_smem_kb, 220) * 1024;
-        int cap = std::min(((smem - 64) / SS::per_candidate) & ~3, LIST_IDX_MASK - 1);
-        *smem_out = cap * SS::per_candidate;
-        *cap_out = cap;
-        return cap >= 64 ? SPHB200_OK : fail(SPHB200_EINVAL, "list shared-memory budget too small");
-    }
-    template <int PASS, bool GEN>
-    int launch_list_t(int epilogue) {
-        auto kern = k_interact_list<T, D, PASS, GEN, BT>;
-        int smem, cap, rc;
-        if ((rc = list_geometry<PASS, GEN>(&smem, &cap))) return rc;
-        static int configured_smem = -1, ctas_per_sm = 0;
-        if (configured_smem != smem) {
+    // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) + occupancy, once per kernel, smem size and HANDLE
+    // (the attribute is per device; a handle is bound to one device)
+    template <class K>
+    int configure_kernel(K kern, int threads, int smem, int *ctas_per_sm) {
+        auto it = kernel_cfg.find((const void *)kern);
+        if (it == kernel_cfg.end() || it->second.first != smem) {
+            int ctas = 0;
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, BT, smem));
-            configured_smem = smem;
-            if (ctas_per_sm < 1) return fail(SPHB200_ECUDA, "list kernel does not fit on an SM");
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, threads, smem));
+            if (ctas < 1) return fail(SPHB200_ECUDA, "kernel does not fit on an SM (%d threads, %d B shared memory)", threads, smem);
+            kernel_cfg[(const void *)kern] = std::make_pair(smem, ctas);
+            *ctas_per_sm = ctas;
+        } else {
+            *ctas_per_sm = it->second.second;
         }
-        InteractArgs<T, D> g;
-        fill_args(g, PASS, epilogue);
-        g.list_cap_cand = cap;
+        return SPHB200_OK;
+    }
+    int persistent_blocks(int ctas_per_sm) const {
         int blocks = num_sms * ctas_per_sm;
         int64_t maxb = (n + BT - 1) / BT + (int64_t)row_cap;
         if ((int64_t)blocks > maxb) blocks = (int)std::max<int64_t>(1, maxb);
-        kern<<<blocks, BT, smem, stream>>>(g);
+        return blocks;
+    }
+    // the list kernel: one persistent CTA per SM (producer warp + consumer warps over a ring of windows)
+    template <int PASS, bool GEN>
+    int launch_ring_t(int epilogue) {
+        using RG = RingGeom<T, D, GEN>;
+        auto kern = k_interact_ring<T, D, PASS, GEN>;
+        int ctas = 0, rc;
+        if ((rc = configure_kernel(kern, RG::THREADS, RG::SMEM, &ctas))) return rc;
+        InteractArgs<T, D> g;
+        fill_args(g, PASS, epilogue);
+        kern<<<persistent_blocks(1), RG::THREADS, RG::SMEM, stream>>>(g);
         ++launches;
         CK(cudaGetLastError());
         return SPHB200_OK;
     }
 
-    // the physics-free list build (runs only when k_step_control raised ctl->list_build)
+    // the physics-free list build + the bank-aware reorder (both run only when k_step_control raised ctl->list_build)
     template <bool GEN>
     int launch_list_build() {
-        return opt_list_order ? launch_list_build_t<GEN, true>() : launch_list_build_t<GEN, false>();
-    }
-    template <bool GEN, bool ORDER>
-    int launch_list_build_t() {
-        auto kern = k_list_build<T, D, GEN, BT, ORDER>;
-        const int list_bytes = LIST_CAP * BT * 2 * (ORDER ? 2 : 1);   // append buffer (+ ordering scratch)
+        auto kern = k_list_build<T, D, GEN, BT>;
+        const int list_bytes = LIST_CAP * BT * 2;   // append buffer
         int smem = std::min(opt_smem_kb, 200) * 1024;
         int cap = std::min(((smem - 64) / (int)sizeof(TA)) & ~3, 32764);
         smem = cap * (int)sizeof(TA) + list_bytes;
-        static int configured_smem = -1, ctas_per_sm = 0;
-        if (configured_smem != smem) {
-            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, BT, smem));
-            configured_smem = smem;
-            if (ctas_per_sm < 1) return fail(SPHB200_ECUDA, "list-build kernel does not fit on an SM");
-        }
+        int ctas = 0, rc;
+        if ((rc = configure_kernel(kern, BT, smem, &ctas))) return rc;
         InteractArgs<T, D> g;
         fill_args(g, 0, EPI_FUSED);
         g.cap = cap;
-        int lsmem, lcap_cand, rc;
-        if ((rc = list_geometry<1, GEN>(&lsmem, &lcap_cand))) return rc;   // pass 2 stages ρₙ too: the tighter of the two
-        g.list_cap_cand = lcap_cand;
-        int blocks = num_sms * ctas_per_sm;
-        int64_t maxb = (n + BT - 1) / BT + (int64_t)row_cap;
-        if ((int64_t)blocks > maxb) blocks = (int)std::max<int64_t>(1, maxb);
-        kern<<<blocks, BT, smem, stream>>>(g);
+        kern<<<persistent_blocks(ctas), BT, smem, stream>>>(g);
         ++launches;
         CK(cudaGetLastError());
+        if (opt_list_reorder) {
+            auto rk = k_list_reorder<BT>;
+            const int rsmem = (REORDER_MAX_SLOTS + REORDER_OVF_CAP) * BT * 2;
+            if ((rc = configure_kernel(rk, BT, rsmem, &ctas))) return rc;
+            rk<<<persistent_blocks(ctas), BT, rsmem, stream>>>(d_ctl.p, d_grid.p, bricks.p, brick_total8.p, nl.p, nl_cnt.p, nl_stride,
+                                                             opt_lcap);
+            ++launches;
+            CK(cudaGetLastError());
+        }
         return SPHB200_OK;
     }
 
@@ -861,25 +891,12 @@ class Sim final : public sphb200_sim {
         cap = std::min(cap, 32764);
         if (cap < 64) return fail(SPHB200_EINVAL, "shared-memory budget too small");
         smem = cap * SS::per_candidate + list_bytes;
-        static int configured_smem = -1;   // per instantiation
-        if (configured_smem != smem) {
-            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            configured_smem = smem;
-        }
-        static int ctas_per_sm = 0;
-        static int ctas_smem = -1;
-        if (ctas_smem != smem) {
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, BT, smem));
-            ctas_smem = smem;
-            if (ctas_per_sm < 1) return fail(SPHB200_ECUDA, "interaction kernel does not fit on an SM");
-        }
+        int ctas = 0, rc;
+        if ((rc = configure_kernel(kern, BT, smem, &ctas))) return rc;
         InteractArgs<T, D> g;
         fill_args(g, PASS, epilogue);
         g.cap = cap;
-        int blocks = num_sms * ctas_per_sm;
-        int64_t maxb = (n + BT - 1) / BT + (int64_t)row_cap;
-        if ((int64_t)blocks > maxb) blocks = (int)std::max<int64_t>(1, maxb);
-        kern<<<blocks, BT, smem, stream>>>(g);
+        kern<<<persistent_blocks(ctas), BT, smem, stream>>>(g);
         ++launches;
         CK(cudaGetLastError());
         return SPHB200_OK;
@@ -892,8 +909,8 @@ class Sim final : public sphb200_sim {
             if (rc) return rc;
             if (pass == 0 && brick_part != 2 && (rc = generic ? launch_list_build<true>() : launch_list_build<false>())) return rc;
             if ((rc = launch_cull(pass, epilogue, 0))) return rc;
-            if (generic) return pass ? launch_list_t<1, true>(epilogue) : launch_list_t<0, true>(epilogue);
-            return pass ? launch_list_t<1, false>(epilogue) : launch_list_t<0, false>(epilogue);
+            if (generic) return pass ? launch_ring_t<1, true>(epilogue) : launch_ring_t<0, true>(epilogue);
+            return pass ? launch_ring_t<1, false>(epilogue) : launch_ring_t<0, false>(epilogue);
         }
         return launch_cull(pass, epilogue, 1);
     }

@@ -18,6 +18,8 @@ ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsphb200.so")
+if os.environ.get("SPHB200_LIB"):          # a variant build (tuning sweeps, scripts/build_variants.sh); never built implicitly
+    LIB_PATH = os.path.abspath(os.environ["SPHB200_LIB"])
 HEADER = os.path.join(ROOT, "include", "sphb200.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -32,6 +34,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """nvcc cross-compiles for sm_100a (works without a GPU)."""
     deps = sources() + [HEADER]
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(f) > os.path.getmtime(LIB_PATH) for f in deps)
+    if os.environ.get("SPHB200_LIB"):
+        stale = force = False
     if force or stale:
         os.makedirs(LIB_DIR, exist_ok=True)
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

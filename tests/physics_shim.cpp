@@ -16,6 +16,9 @@ static void run(const sphb200_params *prm, int n, const double *pos, const doubl
         accum_zero(s);
         T fd = T(0), fa[D];
         for (int k = 0; k < D; ++k) fa[k] = T(0);
+        FastSums<T, D> fs;
+        fast_zero(fs);
+        FastTarget<T> ft = make_fast_target<T>(ph, (T)rho[a], (T)press[a], (T)rho_n[a], (T)ml[a], false);
         PairSide<T, D> A;
         for (int k = 0; k < D; ++k) { A.x[k] = (T)pos[a * D + k]; A.v[k] = (T)vel[a * D + k]; A.vn[k] = (T)vel_n[a * D + k]; }
         A.rho = (T)rho[a]; A.P = (T)press[a]; A.rho_n = (T)rho_n[a]; A.ml = (T)ml[a];
@@ -29,11 +32,9 @@ static void run(const sphb200_params *prm, int n, const double *pos, const doubl
             if (!(r2 <= ph.H2)) continue;
             bool role = a_is_i[(size_t)a * n + b] != 0;
             if (generic) pair_generic<T, D>(ph, A, B, xab, r2, role, s);
-            else {
-                FastTarget<T> ft = make_fast_target<T>(ph, A.rho, A.P, A.rho_n, A.ml, false);
-                pair_fast<T, D, false>(ph, ft, xab, r2, A.v, B.v, B.rho, B.P, B.rho_n, B.ml > T(0), role, fd, fa);
-            }
+            else pair_fast<T, D, false>(ph, ft, xab, r2, A.v, B.v, B.rho, B.P, B.rho_n, B.ml > T(0), role, fs);
         }
+        if (!generic) fast_finish<T, D>(ft, fs, fd, fa);
         drho[a] = generic ? (double)s.drho : (double)fd;
         for (int k = 0; k < D; ++k) acc[a * D + k] = generic ? (double)s.acc[k] : (double)fa[k];
         if (aux) {   // [divr, ksum, gradC[D], kgrad[D]]
@@ -109,6 +110,8 @@ extern "C" int shim_pair_sums_masked(const sphb200_params *prm, int n, const dou
         Phys<T> ph = phys_from_params<T>(*prm);
         for (int a = 0; a < n; ++a) {
             T fd = T(0), fa[D] = {T(0), T(0), T(0)};
+            FastSums<T, D> fs;
+            fast_zero(fs);
             T xa[D], va[D];
             for (int k = 0; k < D; ++k) { xa[k] = (T)pos[a * D + k]; va[k] = (T)vel[a * D + k]; }
             FastTarget<T> ft = make_fast_target<T>(ph, (T)rho[a], (T)press[a], (T)rho_n[a], (T)ml[a], false);
@@ -116,9 +119,10 @@ extern "C" int shim_pair_sums_masked(const sphb200_params *prm, int n, const dou
                 T xab[D], vb[D], r2 = T(0);
                 for (int k = 0; k < D; ++k) { xab[k] = xa[k] - (T)pos[b * D + k]; vb[k] = (T)vel[b * D + k]; r2 += xab[k] * xab[k]; }
                 // b == a included on purpose: the self pair contributes exact zeros on the fast path
-                pair_fast<T, D, false, true>(ph, ft, xab, r2, va, vb, (T)rho[b], (T)press[b], (T)rho_n[b], ml[b] > 0.0,
-                                             a_is_i[(size_t)a * n + b] != 0, fd, fa);
+                pair_fast<T, D, false>(ph, ft, xab, r2, va, vb, (T)rho[b], (T)press[b], (T)rho_n[b], ml[b] > 0.0,
+                                       a_is_i[(size_t)a * n + b] != 0, fs);
             }
+            fast_finish<T, D>(ft, fs, fd, fa);
             drho[a] = (double)fd;
             for (int k = 0; k < D; ++k) acc[a * D + k] = (double)fa[k];
         }
@@ -163,13 +167,16 @@ extern "C" void shim_control_trace(int n, const double *disp2, const double *vis
 
 // ---- bank-aware list ordering (sphexample_b200/csrc/sph_listorder.h) ----
 #include "../sphexample_b200/csrc/sph_listorder.h"
-// reorders entries[0..m) (m <= 64) for lane q exactly as k_list_build's flush does; returns pulls done
-extern "C" int shim_bank_rotate(const unsigned short *entries, int m, int q, unsigned short *out) {
-    unsigned short tmp[64];
-    BankRotator rot;
-    rot.prepare(m, q, [&](int k) -> unsigned { return entries[k]; }, [&](int p) -> unsigned short & { return tmp[p]; });
-    for (int k = 0; k < m; ++k) out[k] = (unsigned short)rot.pull(k, [&](int p) -> unsigned short & { return tmp[p]; });
-    return m;
+// reorders one particle's list (n_slots entries, a multiple of 8, padded with indices >= total8) for lane
+// phase q exactly as k_list_reorder does; returns 1 on success, 0 when the overflow scratch was too small
+extern "C" int shim_rainbow_order(const unsigned short *entries, int n_slots, int q, unsigned total8, int ovf_cap,
+                                  unsigned short *out) {
+    unsigned short ovf[256];
+    if (ovf_cap > 256) ovf_cap = 256;
+    const bool ok = rainbow_order(
+        n_slots, q, total8, [&](int k) -> unsigned { return entries[k]; },
+        [&](int c, int u) -> unsigned short & { return out[c * 8 + u]; }, [&](int p) -> unsigned short & { return ovf[p]; }, ovf_cap);
+    return ok ? 1 : 0;
 }
 
 // step-by-step variant of shim_control_trace for tests whose particle motion depends on the dt decided here

@@ -119,19 +119,17 @@ def test_list_path_equals_cull_path_at_full_size(c3):
         util.check(util.relerr(s1[f], s0[f]), 2e-4)
 
 
-@pytest.mark.xfail(reason="list_order is experimental and off by default: written after round 1's GPU budget was spent, "
-                          "never run on hardware (CPU tests cover its ordering logic); an XPASS here validates it", strict=False)
 @pytest.mark.parametrize("name", ["c1_2d_f64", "3d_f32"])
 def test_bank_ordered_lists_give_the_same_physics(name):
-    """list_order=1 (experimental, csrc/sph_listorder.h): the build hands each lane its entries in a
-    bank-friendly order; only the summation order may change"""
+    """list_reorder (default on; csrc/sph_listorder.h, k_list_reorder): every list is rewritten in a
+    bank-friendly order after a build; only the summation order may change"""
     mk = {"c1_2d_f64": lambda: util.case_c1("float64"), "3d_f32": lambda: util.case_3d_small("float32")}[name]
     out = {}
     for order in (0, 1):
         case = util.perturb(mk(), vel_scale=2.0)
         sim = Simulation(util.params_of(case))
         sim.set_option("lists", 1)
-        sim.set_option("list_order", order)
+        sim.set_option("list_reorder", order)
         sim.upload(case.particles)
         rep = sim.step(80, reset_delta_x=True)
         out[order] = (rep, sim.download(order="id", fields=("Position", "Velocity", "Density")), sim.stat("list_builds"),
