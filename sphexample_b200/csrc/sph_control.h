@@ -29,7 +29,7 @@ struct Ctl {
     int do_rebuild;            // this step runs UpdateNeighbors!
     int error;                 // sticky SPHB200_E* code; every kernel returns early when set
     int step_open;             // step_control ran, step_end has not
-    int pad0;
+    int red_ready;             // the reductions below were produced by the fused pass-2 epilogue of the previous step (k_reduce_dt_dx skips)
     // reductions feeding Δt and Δx (bit patterns of non-negative reals, atomicMax-ed)
     unsigned long long red_disp2, red_visc, red_acc2;
     unsigned long long red_err;   // slab mode: max over ranks of -error (all-reduced with the three above)
@@ -105,6 +105,7 @@ SPH_HD void step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, double list
     ctl->red_disp2 = 0ull;
     ctl->red_visc = 0ull;
     ctl->red_acc2 = 0ull;
+    ctl->red_ready = 0;
     if (ctl->use_target && !(ctl->total_time <= ctl->target_time)) {
         ctl->done = 1;
         return;
@@ -175,6 +176,7 @@ SPH_HD void step_end(Ctl *ctl) {
     ctl->current_dt = ctl->dt;
     ctl->total_time += ctl->dt;
     ctl->step_open = 0;
+    ctl->red_ready = 1;   // the fused corrector of pass 2 has accumulated the Δt / Δx reductions of the new state
 }
 
 }  // namespace sph

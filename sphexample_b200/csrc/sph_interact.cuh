@@ -34,6 +34,7 @@
 
 #include "sph_device.cuh"
 #include "sph_listorder.h"
+#include "sph_step.cuh"
 
 namespace sph {
 
@@ -126,7 +127,7 @@ __device__ __forceinline__ void signal_boundary_brick(const InteractArgs<T, D> &
 // half / full update, shared by the cull kernel and the list kernel.
 template <class T, int D, int PASS, bool GENERIC>
 __device__ __forceinline__ void interact_epilogue(const InteractArgs<T, D> &g, int i, const T *xa, const T *va, T rho_a,
-                                                  const PairAccum<T, D> &sacc, T drho, T *acc) {
+                                                  const PairAccum<T, D> &sacc, T drho, T *acc, StepRed<T> &red) {
     using L = Lay<T, D>;
     using TA = typename L::TA;
     using TB = typename L::TB;
@@ -170,6 +171,9 @@ __device__ __forceinline__ void interact_epilogue(const InteractArgs<T, D> &g, i
 #pragma unroll
             for (int k = 0; k < D; ++k) gc[k] = GENERIC ? sacc.gradC[k] : T(0);
             full_step<T, D>(ph, xn, vn, acc, rho, drho, rho_a, gf, ml, dt, gc, GENERIC ? sacc.divr : T(0));
+            // S0 / S1 of the NEXT step (update_delta_x!, Δt: src/SPHCellList.jl:706-724, src/TimeStepping.jl:24-46)
+            // on the state just produced; xa is this step's half-step position
+            step_red_particle<T, D>(red, xn, vn, acc, xa, true, ph.h, ph.eta2);
             TA oa;
             TB ob;
             L::pack(oa, ob, xn, vn, ml > T(0) ? rho : -rho, eos_gamma7(ph, rho));
@@ -224,6 +228,8 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
     const int brick_first = g.brick_part == 2 ? g.grid->nbricks_bnd : 0;
     const int brick_end = g.brick_part == 1 ? g.grid->nbricks_bnd : nbricks;
     const int npad = (g.grid->n_total + 3) & ~3;
+    StepRed<T> red;   // fused corrector (pass 2): Δt / Δx reductions of the new state
+    step_red_zero(red);
 
     for (;;) {
         if (tid == 0) s_brick = brick_first + atomicAdd(&g.ctl->work_counter[g.counter_slot], 1);
@@ -498,10 +504,11 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
 
         // ---- epilogue ---------------------------------------------------------------------
         if (!GENERIC) fast_finish<T, D>(ft, fs, drho, acc);
-        if (valid) interact_epilogue<T, D, PASS, GENERIC>(g, i, xa, va, rho_a, sacc, drho, acc);
+        if (valid) interact_epilogue<T, D, PASS, GENERIC>(g, i, xa, va, rho_a, sacc, drho, acc, red);
         __syncthreads();   // s_brick / s_off reuse
         signal_boundary_brick(g, bidx, PASS);
     }
+    if (PASS == 1 && g.epilogue == EPI_FUSED) step_red_commit(g.ctl, red);
 }
 
 }  // namespace sph

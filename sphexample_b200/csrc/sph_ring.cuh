@@ -36,6 +36,12 @@
 #ifndef SPH_RING_NCW
 #define SPH_RING_NCW 8
 #endif
+#ifndef SPH_RING_PACKED
+#define SPH_RING_PACKED 1
+#endif
+#ifndef SPH_RING_LIST_PF
+#define SPH_RING_LIST_PF 3
+#endif
 
 namespace sph {
 
@@ -225,35 +231,41 @@ __global__ void __launch_bounds__(BT) k_list_build(const InteractArgs<T, D> g) {
                 const unsigned wlen = (unsigned)(hi - lo);
                 const unsigned role_const = rowrole > 0 ? (unsigned)ROLE_BIT : 0u;
                 const unsigned self_off = (unsigned)(i - cs_a);
-                const bool same_row = rowrole == 0;
-                for (int j4 = jb; j4 < je; j4 += 4) {
+                // (two instantiations of the walk: the per-candidate role logic of the target's own row
+                //  costs 6 issue slots per candidate even when predicated off)
+                auto walk = [&](auto same_row_tag) {
+                    constexpr bool SAME_ROW = decltype(same_row_tag)::value;
+                    for (int j4 = jb; j4 < je; j4 += 4) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int j = j4 + u;
-                        T xb[D];
-                        L::pos(sA[j + sbase], xb);
-                        T r2 = T(0);
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = j4 + u;
+                            T xb[D];
+                            L::pos(sA[j + sbase], xb);
+                            T r2 = T(0);
 #pragma unroll
-                        for (int k = 0; k < D; ++k) {
-                            T dlt = xa[k] - xb[k];
-                            r2 += dlt * dlt;
+                            for (int k = 0; k < D; ++k) {
+                                T dlt = xa[k] - xb[k];
+                                r2 += dlt * dlt;
+                            }
+                            bool ok = (r2 <= Hs2) & ((unsigned)(j - lo) < wlen);
+                            if (GENERIC) ok &= (j != i);
+                            unsigned code = (unsigned)(j + (int)(role_const - (unsigned)jbase));
+                            if (SAME_ROW)
+                                code = (unsigned)(j - jbase) | (((j < ce_a) & ((unsigned)(j - cs_a) > self_off)) ? (unsigned)ROLE_BIT : 0u);
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t"
+                                "setp.ne.u32 p, %2, 0;\n\t"
+                                "@p st.shared.u16 [%0], %1;\n\t"
+                                "@p add.u32 %0, %0, %3;\n\t}"
+                                : "+r"(waddr)
+                                : "h"((unsigned short)code), "r"((unsigned)ok), "n"(BT * 2)
+                                : "memory");
                         }
-                        bool ok = (r2 <= Hs2) & ((unsigned)(j - lo) < wlen);
-                        if (GENERIC) ok &= (j != i);
-                        unsigned code = (unsigned)(j + (int)(role_const - (unsigned)jbase));
-                        if (same_row)
-                            code = (unsigned)(j - jbase) | (((j < ce_a) & ((unsigned)(j - cs_a) > self_off)) ? (unsigned)ROLE_BIT : 0u);
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\t"
-                            "setp.ne.u32 p, %2, 0;\n\t"
-                            "@p st.shared.u16 [%0], %1;\n\t"
-                            "@p add.u32 %0, %0, %3;\n\t}"
-                            : "+r"(waddr)
-                            : "h"((unsigned short)code), "r"((unsigned)ok), "n"(BT * 2)
-                            : "memory");
+                        if (__any_sync(0xffffffffu, waddr > waddr_full)) flush(false);
                     }
-                    if (__any_sync(0xffffffffu, waddr > waddr_full)) flush(false);
-                }
+                };
+                if (rowrole == 0) walk(std::true_type{});
+                else walk(std::false_type{});
             }
             __syncthreads();   // everyone is done with this stage's shared memory
         }
@@ -427,6 +439,93 @@ __global__ void k_list_diag(const GridInfo *grid, const Brick *__restrict__ bric
 }
 
 // =================================================================================================
+// pair_fast (sph_physics.cuh) for TWO list entries at once in packed fp32 (sm_100 FFMA2 / FMUL2 /
+// FADD2: two IEEE fp32 operations per issue slot).  The list kernel is bound by issue slots, not by
+// the fp32 pipe (profiles/r2e: 70 % issue-active, 47 % fma pipe), and FFMA2 runs at half the FFMA
+// rate (scripts/ubench: 1.98 vs 3.81 warp-instructions per clock and SM) — same flops, half the
+// slots.  Lane-wise the operations, their order and their rounding are exactly those of pair_fast:
+// the results are bit-identical to the scalar body.  The two entries' first-level differences and
+// the MUFU results are produced by scalar instructions straight into the halves of register pairs.
+// S3 is accumulated with the opposite sign (fast_finish2 folds the sign into its scale).
+// =================================================================================================
+template <int D>
+struct FastSums2 {
+    float2 s1, s2, s3n[D];
+};
+template <int D>
+__device__ __forceinline__ void fast_zero2(FastSums2<D> &s) {
+    s.s1 = s.s2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < D; ++k) s.s3n[k] = make_float2(0.f, 0.f);
+}
+template <int D>
+__device__ __forceinline__ void fast_finish2(const FastTarget<float> &a, const FastSums2<D> &s, float &drho, float *acc) {
+    drho = a.k_cont * (s.s1.x + s.s1.y) + a.k_ddt * (s.s2.x + s.s2.y);
+#pragma unroll
+    for (int k = 0; k < D; ++k) acc[k] = -a.k_acc * (s.s3n[k].x + s.s3n[k].y);
+}
+struct FastConst2 {   // broadcast pairs of the per-target / per-run constants
+    float2 h_inv, m2, eta2, rhon, m_rhon, m_ddt_lin, P, c_visc_n;
+};
+__device__ __forceinline__ FastConst2 make_fast_const2(const Phys<float> &p, const FastTarget<float> &a) {
+    FastConst2 c;
+    c.h_inv = make_float2(p.h_inv, p.h_inv);
+    c.m2 = make_float2(-2.f, -2.f);
+    c.eta2 = make_float2(p.eta2, p.eta2);
+    c.rhon = make_float2(a.rhon, a.rhon);
+    c.m_rhon = make_float2(-a.rhon, -a.rhon);
+    c.m_ddt_lin = make_float2(-p.ddt_lin, -p.ddt_lin);
+    c.P = make_float2(a.P, a.P);
+    c.c_visc_n = make_float2(-a.c_visc, -a.c_visc);
+    return c;
+}
+// xab / vab: x_a − x_b and v_a − v_b of the two entries; rs_b: their signed densities (sign = fluid);
+// rhon_b: their state-n densities (pass 2; ignored when SAME_RHO)
+template <int D, bool SAME_RHO>
+__device__ __forceinline__ void pair_fast_x2(const FastTarget<float> &a, const FastConst2 &c, const float2 *xab, const float2 *vab,
+                                             float2 rs_b, float2 P_b, float2 rhon_b, bool role0, bool role1, FastSums2<D> &s) {
+    float2 r2 = __fmul2_rn(xab[0], xab[0]);
+    float2 vdotx = __fmul2_rn(vab[0], xab[0]);
+#pragma unroll
+    for (int k = 1; k < D; ++k) {
+        r2 = __ffma2_rn(xab[k], xab[k], r2);
+        vdotx = __ffma2_rn(vab[k], xab[k], vdotx);
+    }
+    const float2 d = make_float2(sph_sqrt_fast(r2.x), sph_sqrt_fast(r2.y));
+    float2 qm2 = __ffma2_rn(d, c.h_inv, c.m2);
+    qm2.x = fminf(qm2.x, 0.f);
+    qm2.y = fminf(qm2.y, 0.f);
+    const float2 fac = __fmul2_rn(qm2, __fmul2_rn(qm2, qm2));
+    const float2 irb = make_float2(sph_rcp(fabsf(rs_b.x)), sph_rcp(fabsf(rs_b.y)));
+    float2 irnb = irb, sum_rhon, dr;
+    if (SAME_RHO) {
+        sum_rhon = make_float2(a.rhon + fabsf(rs_b.x), a.rhon + fabsf(rs_b.y));
+        dr = make_float2(fabsf(rs_b.x) - a.rhon, fabsf(rs_b.y) - a.rhon);
+    } else {
+        irnb = make_float2(sph_rcp(rhon_b.x), sph_rcp(rhon_b.y));
+        sum_rhon = __fadd2_rn(c.rhon, rhon_b);
+        dr = __fadd2_rn(rhon_b, c.m_rhon);
+    }
+    s.s1 = __ffma2_rn(__fmul2_rn(irb, fac), vdotx, s.s1);
+    const float2 den = __fmul2_rn(__fadd2_rn(r2, c.eta2), sum_rhon);
+    const float2 ip = make_float2(sph_rcp(den.x), sph_rcp(den.y));   // 1 / ((r²+η²)(ρₙ_a+ρₙ_b))
+    const float2 inv = __fmul2_rn(ip, sum_rhon);                     // 1 / (r²+η²)
+    const float2 diff = __ffma2_rn(c.m_ddt_lin, xab[D - 1], dr);
+    float2 V;
+    V.x = role0 ? irnb.x : a.inv_rhon;
+    V.y = role1 ? irnb.y : a.inv_rhon;
+    V.x = rs_b.x > 0.f ? V.x : 0.f;
+    V.y = rs_b.y > 0.f ? V.y : 0.f;
+    s.s2 = __ffma2_rn(V, __fmul2_rn(diff, __fmul2_rn(__fmul2_rn(fac, r2), inv)), s.s2);
+    const float2 mn = make_float2(fminf(vdotx.x, 0.f), fminf(vdotx.y, 0.f));
+    const float2 pq = __fmul2_rn(__fadd2_rn(c.P, P_b), irb);
+    const float2 c1n = __ffma2_rn(c.c_visc_n, __fmul2_rn(mn, ip), pq);   // −(c_visc min(v·x,0) ip − (P_a+P_b)/ρ_b)
+    const float2 cfn = __fmul2_rn(c1n, fac);
+#pragma unroll
+    for (int k = 0; k < D; ++k) s.s3n[k] = __ffma2_rn(cfn, xab[k], s.s3n[k]);
+}
+
+// =================================================================================================
 // The LIST kernel (see the file header).
 // =================================================================================================
 template <class T, int D, int PASS, bool GENERIC>
@@ -438,7 +537,8 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
     using SS = StageSizes<T, D, PASS, GENERIC>;
     constexpr int NR = (D == 3) ? 9 : 3;
     constexpr int NSLOT = RG::NSLOT, CAP = RG::CAP, NCW = RG::NCW;
-    constexpr int LIST_PF = 3;   // list chunks in flight per lane
+    constexpr int LIST_PF = SPH_RING_LIST_PF;   // list chunks in flight per lane
+    constexpr bool PACKED = !GENERIC && std::is_same<T, float>::value && SPH_RING_PACKED;   // pair_fast_x2
     constexpr int OFF_B = CAP * SS::esA, OFF_R = OFF_B + CAP * SS::esB, OFF_BN = OFF_R + CAP * SS::esR;
     static_assert(OFF_BN + CAP * SS::esBn <= RG::SLOT_BYTES, "ring slot too small");
 
@@ -571,6 +671,8 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
     // =========================== consumer warps =================================================
     const int nbnd = g.bnd_flag ? g.grid->nbricks_bnd : 0;
     const T H2 = ph.H2;
+    StepRed<T> red;   // fused corrector (pass 2): Δt / Δx reductions of the new state, one commit per warp
+    step_red_zero(red);
     for (int seq = 0;; ++seq) {
         const int slot = seq % NSLOT;
         const uint32_t use = (uint32_t)(seq / NSLOT);
@@ -652,6 +754,12 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
             const FastTarget<T> ft = make_fast_target<T>(ph, rho_a, P_a, rhon_a, ml_a, PASS == 0);
             FastSums<T, D> fs;
             fast_zero(fs);
+            [[maybe_unused]] FastSums2<D> fs2;
+            [[maybe_unused]] FastConst2 fc2;
+            if constexpr (PACKED) {
+                fast_zero2(fs2);
+                fc2 = make_fast_const2(ph, ft);
+            }
 
             const int mchunk = warp_max(nchunk);
             // one chunk of 8 entries; lanes whose list has ended run the padding chunk: the warp stays converged
@@ -672,20 +780,40 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
                         b8[u] = sB[sj];
                         if (PASS) r8[u] = sR[sj];
                     }
+                    if constexpr (PACKED) {
+                        // two entries per packed body (one 32-bit list word = the two entries)
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const unsigned w = w4[u >> 1];
-                        const bool a_is_i = (u & 1) ? ((int)w < 0) : ((w & 0x8000u) != 0u);
-                        T xb[D], vb[D], rsb, P_b;
-                        L::unpack(a8[u], b8[u], xb, vb, rsb, P_b);
-                        T xab[D], r2 = T(0);
+                        for (int u = 0; u < 8; u += 2) {
+                            const unsigned w = w4[u >> 1];
+                            float x0[D], v0[D], x1[D], v1[D], rs0, rs1, P0, P1;
+                            L::unpack(a8[u], b8[u], x0, v0, rs0, P0);
+                            L::unpack(a8[u + 1], b8[u + 1], x1, v1, rs1, P1);
+                            float2 xab2[D], vab2[D];
 #pragma unroll
-                        for (int k = 0; k < D; ++k) {
-                            xab[k] = xa[k] - xb[k];
-                            r2 += xab[k] * xab[k];
+                            for (int k = 0; k < D; ++k) {
+                                xab2[k] = make_float2(xa[k] - x0[k], xa[k] - x1[k]);
+                                vab2[k] = make_float2(va[k] - v0[k], va[k] - v1[k]);
+                            }
+                            pair_fast_x2<D, PASS == 0>(ft, fc2, xab2, vab2, make_float2(rs0, rs1), make_float2(P0, P1),
+                                                       PASS ? make_float2(r8[u], r8[u + 1]) : make_float2(0.f, 0.f),
+                                                       (w & 0x8000u) != 0u, (int)w < 0, fs2);
                         }
-                        const T rho_b = sph_abs(rsb);
-                        pair_fast<T, D, PASS == 0>(ph, ft, xab, r2, va, vb, rho_b, P_b, PASS ? r8[u] : rho_b, rsb > T(0), a_is_i, fs);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const unsigned w = w4[u >> 1];
+                            const bool a_is_i = (u & 1) ? ((int)w < 0) : ((w & 0x8000u) != 0u);
+                            T xb[D], vb[D], rsb, P_b;
+                            L::unpack(a8[u], b8[u], xb, vb, rsb, P_b);
+                            T xab[D], r2 = T(0);
+#pragma unroll
+                            for (int k = 0; k < D; ++k) {
+                                xab[k] = xa[k] - xb[k];
+                                r2 += xab[k] * xab[k];
+                            }
+                            const T rho_b = sph_abs(rsb);
+                            pair_fast<T, D, PASS == 0>(ph, ft, xab, r2, va, vb, rho_b, P_b, PASS ? r8[u] : rho_b, rsb > T(0), a_is_i, fs);
+                        }
                     }
                 } else {
 #pragma unroll 2
@@ -733,8 +861,9 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
             T drho = T(0), acc[D];
 #pragma unroll
             for (int k = 0; k < D; ++k) acc[k] = T(0);
-            if (!GENERIC) fast_finish<T, D>(ft, fs, drho, acc);
-            if (valid) interact_epilogue<T, D, PASS, GENERIC>(g, i, xa, va, rho_a, sacc, drho, acc);
+            if constexpr (PACKED) fast_finish2<D>(ft, fs2, drho, acc);
+            else if (!GENERIC) fast_finish<T, D>(ft, fs, drho, acc);
+            if (valid) interact_epilogue<T, D, PASS, GENERIC>(g, i, xa, va, rho_a, sacc, drho, acc, red);
 
             if (bidx < nbnd) {
                 // slab mode: the warp that retires the last sub-brick of the last boundary brick
@@ -752,6 +881,7 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[slot]);
     }
+    if (PASS == 1 && g.epilogue == EPI_FUSED) step_red_commit(g.ctl, red);
 }
 
 }  // namespace sph

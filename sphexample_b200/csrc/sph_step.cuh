@@ -15,58 +15,84 @@ namespace sph {
 // min over i of sqrt(h/‖aᵢ‖) == sqrt(h / max ‖aᵢ‖) (monotone), so one max serves.
 // warp shuffle -> one atomicMax per warp on the bit pattern (all three are non-negative).
 // ---------------------------------------------------------------------------------------------
+template <class T>
+struct StepRed {
+    T disp2, visc, acc2, vel2;
+    bool nan;
+};
+template <class T>
+__device__ __forceinline__ void step_red_zero(StepRed<T> &r) {
+    r.disp2 = r.visc = r.acc2 = r.vel2 = T(0);
+    r.nan = false;
+}
+// one particle's terms: x, v, a of the (new) state n, xh = the half-step position (have_half)
+template <class T, int D>
+__device__ __forceinline__ void step_red_particle(StepRed<T> &r, const T *x, const T *v, const T *a, const T *xh, bool have_half,
+                                                  T h, T eta2) {
+    T vx = T(0), xx = T(0), aa = T(0), dd = T(0), vv = T(0);
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        vx += v[k] * x[k];
+        xx += x[k] * x[k];
+        aa += a[k] * a[k];
+        vv += v[k] * v[k];
+    }
+    if (have_half) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            T d = xh[k] - x[k];
+            dd += d * d;
+        }
+    }
+    T visc = sph_abs(h * vx / (xx + eta2));
+    r.nan |= !(visc == visc) || !(aa == aa) || !(dd == dd);
+    r.disp2 = sph_max(r.disp2, dd);
+    r.visc = sph_max(r.visc, visc);
+    r.acc2 = sph_max(r.acc2, aa);
+    r.vel2 = sph_max(r.vel2, vv);
+}
+// whole warp: shuffle reduction, then one atomicMax per quantity on the bit pattern (all non-negative)
+template <class T>
+__device__ __forceinline__ void step_red_commit(Ctl *ctl, StepRed<T> r) {
+    r.disp2 = warp_max(r.disp2);
+    r.visc = warp_max(r.visc);
+    r.acc2 = warp_max(r.acc2);
+    r.vel2 = warp_max(r.vel2);
+    const bool nan = __any_sync(0xffffffffu, r.nan);
+    if ((threadIdx.x & 31) == 0) {
+        if (nan) {
+            atomicCAS(&ctl->error, 0, SPH_ERR_ENUMERIC);
+        } else {
+            if (r.disp2 > T(0)) atomic_max_nonneg(&ctl->red_disp2, (double)r.disp2);
+            if (r.visc > T(0)) atomic_max_nonneg(&ctl->red_visc, (double)r.visc);
+            if (r.acc2 > T(0)) atomic_max_nonneg(&ctl->red_acc2, (double)r.acc2);
+            if (r.vel2 > T(0)) atomic_max_nonneg(&ctl->red_vel2, (double)r.vel2);
+        }
+    }
+}
+
+// Stand-alone form (first step after an upload, stage-level calls): in the step loop the fused
+// corrector of pass 2 accumulates the same terms in its epilogue (ctl->red_ready) and this kernel
+// returns at once.
 template <class T, int D>
 __global__ void k_reduce_dt_dx(const typename Lay<T, D>::TA *__restrict__ A, const typename Lay<T, D>::TB *__restrict__ B,
                                const typename Lay<T, D>::TA *__restrict__ Ah,
                                const typename Lay<T, D>::TV *__restrict__ acc, int p0, int p1, T h, T eta2,
                                int have_half, Ctl *ctl) {
     using L = Lay<T, D>;
-    if (ctl->error || ctl->done) return;
-    T mdisp = T(0), mvisc = T(0), macc = T(0), mvel = T(0);
-    bool nan = false;
+    if (ctl->error || ctl->done || ctl->red_ready) return;
+    StepRed<T> red;
+    step_red_zero(red);
     for (int i = p0 + blockIdx.x * blockDim.x + threadIdx.x; i < p1; i += gridDim.x * blockDim.x) {
-        T x[D], v[D], rs, P, a[D];
+        T x[D], v[D], rs, P, a[D], xh[D];
         L::unpack(A[i], B[i], x, v, rs, P);
         L::getv(acc[i], a);
-        T vx = T(0), xx = T(0), aa = T(0), dd = T(0), vv = T(0);
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-            vx += v[k] * x[k];
-            xx += x[k] * x[k];
-            aa += a[k] * a[k];
-            vv += v[k] * v[k];
-        }
-        if (have_half) {
-            T xh[D];
-            L::pos(Ah[i], xh);
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                T d = xh[k] - x[k];
-                dd += d * d;
-            }
-        }
-        T visc = sph_abs(h * vx / (xx + eta2));
-        nan |= !(visc == visc) || !(aa == aa) || !(dd == dd);
-        mdisp = sph_max(mdisp, dd);
-        mvisc = sph_max(mvisc, visc);
-        macc = sph_max(macc, aa);
-        mvel = sph_max(mvel, vv);
+        for (int k = 0; k < D; ++k) xh[k] = x[k];
+        if (have_half) L::pos(Ah[i], xh);
+        step_red_particle<T, D>(red, x, v, a, xh, have_half != 0, h, eta2);
     }
-    mdisp = warp_max(mdisp);
-    mvisc = warp_max(mvisc);
-    macc = warp_max(macc);
-    mvel = warp_max(mvel);
-    nan = __any_sync(0xffffffffu, nan);
-    if ((threadIdx.x & 31) == 0) {
-        if (nan) {
-            atomicCAS(&ctl->error, 0, SPH_ERR_ENUMERIC);
-        } else {
-            if (mdisp > T(0)) atomic_max_nonneg(&ctl->red_disp2, (double)mdisp);
-            if (mvisc > T(0)) atomic_max_nonneg(&ctl->red_visc, (double)mvisc);
-            if (macc > T(0)) atomic_max_nonneg(&ctl->red_acc2, (double)macc);
-            if (mvel > T(0)) atomic_max_nonneg(&ctl->red_vel2, (double)mvel);
-        }
-    }
+    step_red_commit(ctl, red);
 }
 
 // One thread: S0/S1 completion, the S2 decision, the while-condition and the neighbour-list state
@@ -82,6 +108,9 @@ __global__ void k_step_end(Ctl *ctl) { step_end(ctl); }
 
 // any change of positions or cells outside the step sequence voids the neighbour lists
 __global__ void k_invalidate_lists(Ctl *ctl) {
+    // (also voids the Δt / Δx reductions a fused pass 2 left behind: the state is about to change)
+    ctl->red_ready = 0;
+    ctl->red_disp2 = ctl->red_visc = ctl->red_acc2 = ctl->red_vel2 = 0ull;
     ctl->list_valid = 0;
     ctl->list_build = 0;
     ctl->list_mode[0] = ctl->list_mode[1] = 0;

@@ -1248,7 +1248,8 @@ class Sim final : public sphb200_sim {
         CK(cudaSetDevice(device));
         int rc = sync_ctl();
         if (rc) return rc;
-        h_ctl->red_disp2 = h_ctl->red_visc = h_ctl->red_acc2 = 0ull;
+        h_ctl->red_disp2 = h_ctl->red_visc = h_ctl->red_acc2 = h_ctl->red_vel2 = 0ull;
+        h_ctl->red_ready = 0;   // whatever a fused pass 2 left behind is recomputed by the next step head
         if ((rc = push_ctl())) return rc;
         k_reduce_dt_dx<T, D><<<grid_for(n), 256, 0, stream>>>(A.p, B.p, Ah.p, acc.p, 0, (int)n, ph.h, ph.eta2, 0, d_ctl.p);
         ++launches;
@@ -1258,7 +1259,7 @@ class Sim final : public sphb200_sim {
         T dt1 = sph_sqrt(ph.h / sph_sqrt(acc2));
         T dt2 = ph.h / (ph.c0 + visc);
         if (dt) *dt = (double)((T)prm.cfl * std::min(dt1, dt2));
-        h_ctl->red_disp2 = h_ctl->red_visc = h_ctl->red_acc2 = 0ull;
+        h_ctl->red_disp2 = h_ctl->red_visc = h_ctl->red_acc2 = h_ctl->red_vel2 = 0ull;
         if ((rc = push_ctl())) return rc;
         CK(cudaStreamSynchronize(stream));
         return SPHB200_OK;
