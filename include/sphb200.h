@@ -151,10 +151,27 @@ int sphb200_set_option(sphb200_sim *sim, const char *name, double value);
 /* run-time counters: "list_builds", "list_off" (1 = lists switched off after an overflow),
  * "halo_bytes_per_step", "migrated", "n_total" (owned + halo particles held) */
 int sphb200_get_stat(sphb200_sim *sim, const char *name, double *value);
-/* device time (ms) of the stages of ONE extra step, the analogue of the reference's TimerOutputs
- * sections (src/SPHCellList.jl:748-800): [0] Δt/Δx reductions + control ("01"), [1] neighbour
- * rebuild + motion + mDBC ("02"-"04"), [2] first NeighborLoop + half step ("05"-"07"),
- * [3] second NeighborLoop + full step ("08"-"11"), [4] metadata ("12").  Advances the simulation. */
+/* Device time (ms, CUDA events) of the stages of ONE extra step — the reference's TimerOutputs
+ * report (SimMetaData.HourGlass, labels "01" .. "12", src/SPHCellList.jl:748-800) with the labels
+ * grouped the way the fused kernels group them.  ms_out[k], k < min(n, SPHB200_N_STAGES); advances
+ * the simulation by one step.  In slab mode the call is collective. */
+enum {
+    SPHB200_STAGE_TIMESTEP = 0,   /* S0/S1 reductions (when not fused into the previous pass 2) + "01 Update TimeStep" + step control */
+    SPHB200_STAGE_REBUILD = 1,    /* "02 Calculate IndexCounter" / "02a": UpdateNeighbors! (predicated on the rebuild flag) */
+    SPHB200_STAGE_MOTION1 = 2,    /* "Motion" (first ProgressMotion) + the state-n snapshots pass 2 reads (Q2) */
+    SPHB200_STAGE_MDBC = 3,       /* "04 Apply MDBC before Half TimeStep" */
+    SPHB200_STAGE_LISTS = 4,      /* neighbour-list build + reorder (predicated; no reference stage) */
+    SPHB200_STAGE_PASS1 = 5,      /* "05 First NeighborLoop" + "03 Pressure" + "06 Update To Half TimeStep" + "07 Half LimitDensityAtBoundary" */
+    SPHB200_STAGE_MOTION2 = 6,    /* "Motion" (second ProgressMotion) */
+    SPHB200_STAGE_PASS2 = 7,      /* "08 Second NeighborLoop" + "03" + "09 Final LimitDensityAtBoundary" + "10 Final Density" + "11 Update To Final TimeStep" (+ the next step's S0/S1 reductions) */
+    SPHB200_STAGE_METADATA = 8,   /* "12 Update MetaData" */
+    SPHB200_STAGE_ALLREDUCE = 9,  /* slab mode: the per-step all-reduce, including the wait for the slowest rank */
+    SPHB200_STAGE_HALO1 = 10,     /* slab mode: duration of the half-step halo exchange of pass 1 (on the exchange stream) */
+    SPHB200_STAGE_HALO1_EXPOSED = 11, /* ... of which not hidden behind the interior bricks */
+    SPHB200_STAGE_HALO2 = 12,     /* slab mode: the same for pass 2 */
+    SPHB200_STAGE_HALO2_EXPOSED = 13,
+    SPHB200_N_STAGES = 16
+};
 int sphb200_stage_times(sphb200_sim *sim, double *ms_out, int n);
 
 /* ---- stage-level entry points (the reference's exported step functions) ------------- */

@@ -27,7 +27,9 @@ for s in sets:
     sim.step(8, reset_delta_x=True)
     import torch
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    st = np.mean([sim.stage_times() for _ in range(6)], axis=0)
+    _t = [sim.stage_times() for _ in range(6)]
+    _v = np.mean([list(t.values()) for t in _t], axis=0)
+    st = [_v[0], _v[1] + _v[2] + _v[3], _v[4] + _v[5], _v[6] + _v[7], _v[8]]   # legacy 5 buckets: head, rebuild+motion, pass 1 (+lists), pass 2, metadata
     b0 = sim.stat("list_builds"); r0 = sim.report()
     K = int(os.environ.get("SPH_STEPS", "60"))
     torch.cuda.synchronize(); e0.record(); sim.step(K); e1.record(); torch.cuda.synchronize()

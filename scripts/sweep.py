@@ -24,7 +24,9 @@ for s in sets:
         sim.set_option(k, float(v))
     sim.upload(case.particles)
     sim.step(8, reset_delta_x=True)
-    st = np.mean([sim.stage_times() for _ in range(6)], axis=0)
+    _t = [sim.stage_times() for _ in range(6)]
+    _v = np.mean([list(t.values()) for t in _t], axis=0)
+    st = [_v[0], _v[1] + _v[2] + _v[3], _v[4] + _v[5], _v[6] + _v[7], _v[8]]   # legacy 5 buckets: head, rebuild+motion, pass 1 (+lists), pass 2, metadata
     print(json.dumps({"opts": opts, "n": len(case.particles), "float": ft, "pass0_ms": st[2], "pass1_ms": st[3],
-                      "reduce_ms": st[0], "rebuild_ms": st[1], "Mpu_s": len(case.particles) / (st.sum() * 1e-3) / 1e6}), flush=True)
+                      "reduce_ms": st[0], "rebuild_ms": st[1], "Mpu_s": len(case.particles) / (sum(st) * 1e-3) / 1e6}), flush=True)
     sim.close()

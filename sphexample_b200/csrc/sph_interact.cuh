@@ -212,7 +212,6 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
     __shared__ int s_w0a[NR], s_len[NR], s_off[NR + 1];
 
     const int tid = threadIdx.x;
-    const int lane = tid & 31;
     const Phys<T> &ph = g.phys;
     const bool use_sps = GENERIC && PASS && (ph.viscosity == V_SPS);
 

@@ -101,7 +101,6 @@ struct SlabComm {
     nccl::comm_t comm = nullptr;
     cudaStream_t xstream = nullptr; // the half-step halo exchanges run here, beside the interior bricks
     cudaEvent_t ev_bnd = nullptr, ev_x = nullptr;
-    cudaEvent_t *dbg_ev = nullptr;  // timing probes of one step (slab_stage_times with SPHB200_SLAB_DEBUG)
     // single-launch passes: the kernel raises *d_flag to `epoch` when its boundary bricks are done,
     // the exchange stream waits for that value (driver API cuStreamWaitValue32)
     unsigned *d_flag = nullptr;

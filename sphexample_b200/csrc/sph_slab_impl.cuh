@@ -313,16 +313,15 @@ int Sim<T, D>::slab_rebuild() {
     return SPHB200_OK;
 }
 
-// S2 .. S19 of one step in slab mode (after the head has been synchronised); ev: optional 6 events
-// bracketing rebuild+motion+snapshots | pass 0 | halo n+1/2 | pass 1 | halo n+1
 // One interaction pass over the owned bricks with its halo exchange hidden behind the interior
 // bricks.  Nothing the exchange writes (the halo ranges of xa/xb) is read, and nothing it reads is
-// written, before the next pass.
+// written, before the next pass.  xev (optional, 4 events, stage_times): [0] pass start (main
+// stream), [1] exchange released, [2] exchange complete (both on the exchange stream), [3] interior
+// bricks done (main stream).
 template <class T, int D>
-int Sim<T, D>::slab_pass(int pass, TA *xa, TB *xb) {
+int Sim<T, D>::slab_pass(int pass, TA *xa, TB *xb, cudaEvent_t *xev) {
     int rc;
-    cudaEvent_t *dbg = slab.dbg_ev ? slab.dbg_ev + pass * 5 : nullptr;   // optional timing probes (SPHB200_SLAB_DEBUG)
-    if (dbg) CKS(cudaEventRecord(dbg[0], stream));
+    if (xev) CKS(cudaEventRecord(xev[0], stream));
     if (slab.wait_value32) {
         // one launch: boundary bricks first, the flag releases the exchange, interior bricks go on
         const unsigned epoch = ++slab.epoch;
@@ -333,34 +332,32 @@ int Sim<T, D>::slab_pass(int pass, TA *xa, TB *xb) {
         if (rc) return rc;
         k_slab_signal<<<1, 1, 0, stream>>>(slab.d_flag, epoch);
         ++launches;
-        if (dbg) CKS(cudaEventRecord(dbg[4], stream));
-        if (dbg) CKS(cudaEventRecord(dbg[1], stream));
+        if (xev) CKS(cudaEventRecord(xev[3], stream));
         // everything that raises the flag is in flight before anything waits on it
         if (slab.wait_value32(slab.xstream, (unsigned long long)(uintptr_t)slab.d_flag, epoch, 0u /* GEQ */) != 0)
             return fail(SPHB200_ECUDA, "cuStreamWaitValue32 failed");
-        if (dbg) CKS(cudaEventRecord(dbg[2], slab.xstream));
+        if (xev) CKS(cudaEventRecord(xev[1], slab.xstream));
         if ((rc = slab_exchange_halo(xa, xb, slab.xstream))) return rc;
         CKS(cudaEventRecord(slab.ev_x, slab.xstream));
-        if (dbg) CKS(cudaEventRecord(dbg[3], slab.xstream));
+        if (xev) CKS(cudaEventRecord(xev[2], slab.xstream));
         CKS(cudaStreamWaitEvent(stream, slab.ev_x, 0));
         return SPHB200_OK;
     }
-    // default: two launches, boundary bricks then interior bricks (validated on 4 GPUs, profiles/r1q_*)
+    // default: two launches, boundary bricks then interior bricks
     brick_part = 1;
     rc = launch_interact(pass, EPI_FUSED);
     if (!rc) {
         CKS(cudaEventRecord(slab.ev_bnd, stream));
-        if (dbg) CKS(cudaEventRecord(dbg[1], stream));
         CKS(cudaStreamWaitEvent(slab.xstream, slab.ev_bnd, 0));
-        if (dbg) CKS(cudaEventRecord(dbg[2], slab.xstream));
+        if (xev) CKS(cudaEventRecord(xev[1], slab.xstream));
         rc = slab_exchange_halo(xa, xb, slab.xstream);
     }
     if (!rc) {
         CKS(cudaEventRecord(slab.ev_x, slab.xstream));
-        if (dbg) CKS(cudaEventRecord(dbg[3], slab.xstream));
+        if (xev) CKS(cudaEventRecord(xev[2], slab.xstream));
         brick_part = 2;
         rc = launch_interact(pass, EPI_FUSED);
-        if (dbg) CKS(cudaEventRecord(dbg[4], stream));
+        if (xev) CKS(cudaEventRecord(xev[3], stream));
     }
     brick_part = 0;
     if (rc) return rc;
@@ -378,24 +375,30 @@ int Sim<T, D>::slab_resume_after_pause() {
     return slab_rebuild();
 }
 
+// S2 .. S19 of one step in slab mode.  ev (optional, 9 events): the stage boundaries of
+// enqueue_step_body; xev (optional, 8 events): the exchange probes of the two passes (slab_pass).
 template <class T, int D>
-int Sim<T, D>::slab_step_body(cudaEvent_t *ev, bool host_synced) {
+int Sim<T, D>::slab_step_body(cudaEvent_t *ev, bool host_synced, cudaEvent_t *xev) {
     int rc;
 #define EV(k) if (ev) CKS(cudaEventRecord(ev[k], stream))
     EV(0);
-    if (host_synced && h_ctl->do_rebuild && (rc = slab_resume_after_pause())) return rc;
+    if (host_synced && h_ctl->do_rebuild && (rc = slab_resume_after_pause())) return rc;   // S2 (needs the host: exchange sizes)
+    EV(1);
     if ((rc = enqueue_motion(-1.0))) return rc;                       // S3
     if ((rc = enqueue_snapshots())) return rc;
-    EV(1);
-    if ((rc = slab_pass(0, Ah.p, Bh.p))) return rc;                   // S4-S10, S13 + halo state n+1/2
-    if ((rc = enqueue_motion(-1.0))) return rc;                       // S12
     EV(2);
     EV(3);
-    if ((rc = slab_pass(1, A.p, B.p))) return rc;                     // S11, S14-S18 + halo state n+1
+    if ((rc = enqueue_list_build())) return rc;
+    EV(4);
+    if ((rc = slab_pass(0, Ah.p, Bh.p, xev))) return rc;              // S4-S10, S13 + halo state n+1/2
+    EV(5);
+    if ((rc = enqueue_motion(-1.0))) return rc;                       // S12
+    EV(6);
+    if ((rc = slab_pass(1, A.p, B.p, xev ? xev + 4 : nullptr))) return rc;   // S11, S14-S18 + halo state n+1
+    EV(7);
     k_step_end<<<1, 1, 0, stream>>>(d_ctl.p);                         // S19
     ++launches;
-    EV(4);
-    EV(5);
+    EV(8);
 #undef EV
     have_half = true;
     have_cells = true;
@@ -452,46 +455,57 @@ int Sim<T, D>::run_steps_slab(int64_t nsteps, bool until_target) {
     return SPHB200_OK;
 }
 
-// slab-mode stage times of ONE extra step (collective): [0] reductions + all-reduce + control,
-// [1] rebuild + motion + snapshots, [2] pass 0, [3] pass 1 (each incl. whatever of its halo exchange
-// the interior bricks did not hide), [4] 0
+// slab-mode stage times of ONE extra step (collective), SPHB200_STAGE_* of include/sphb200.h.  The
+// head is split at the all-reduce: what a rank waits there for the slowest rank is reported as
+// SPHB200_STAGE_ALLREDUCE, not as reduction time.  A pass's time includes whatever of its halo
+// exchange the interior bricks did not hide; the exchange itself is timed on the exchange stream.
 template <class T, int D>
 int Sim<T, D>::slab_stage_times(double *ms_out, int cnt) {
-    cudaEvent_t ev[7];
+    cudaEvent_t ev[9], xev[8], hev[4];
     for (auto &e : ev) CKS(cudaEventCreate(&e));
-    CKS(cudaEventRecord(ev[6], stream));
-    bool stop = false;
-    int rc = slab_check_head(&stop, false);
-    if (rc) return rc;
-    cudaEvent_t dbg[10];
-    const bool debug = getenv("SPHB200_SLAB_DEBUG") != nullptr;
-    if (debug) {
-        for (auto &e : dbg) CKS(cudaEventCreate(&e));
-        slab.dbg_ev = dbg;
-    }
-    rc = slab_step_body(ev);
-    slab.dbg_ev = nullptr;
+    for (auto &e : xev) CKS(cudaEventCreate(&e));
+    for (auto &e : hev) CKS(cudaEventCreate(&e));
+    int rc;
+    // head: reductions | all-reduce | control
+    const int p0 = slab.own_p0, p1 = slab.own_p1;
+    CKS(cudaEventRecord(hev[0], stream));
+    k_reduce_dt_dx<T, D><<<grid_for(p1 - p0), 256, 0, stream>>>(A.p, B.p, Ah.p, acc.p, p0, p1, ph.h, ph.eta2, have_half ? 1 : 0, d_ctl.p);
+    ++launches;
+    CKS(cudaEventRecord(hev[1], stream));
+    if ((rc = slab_allreduce_ctl())) return rc;
+    CKS(cudaEventRecord(hev[2], stream));
+    k_step_control<T><<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, ph.h, ph.c0, (T)prm.cfl, lists_on() ? opt_skin * prm.H : 0.0,
+                                           motion_vmax(), 1);
+    ++launches;
+    CKS(cudaEventRecord(hev[3], stream));
+    if ((rc = sync_ctl())) return rc;
+    if (h_ctl->error) return fail(h_ctl->error, "device reported error %d (rank %d)", h_ctl->error, slab.rank);
+    rc = slab_step_body(ev, true, xev);
     if (rc) return rc;
     CKS(cudaStreamSynchronize(stream));
     CKS(cudaStreamSynchronize(slab.xstream));
-    if (debug) {
-        for (int p = 0; p < 2; ++p) {
-            float pass_ms = 0.f, xstart = 0.f, xend = 0.f;
-            cudaEvent_t *d = dbg + p * 5;
-            cudaEventElapsedTime(&pass_ms, d[0], d[4]);   // the pass's launches on the main stream
-            cudaEventElapsedTime(&xstart, d[0], d[2]);    // exchange released (boundary bricks done)
-            cudaEventElapsedTime(&xend, d[0], d[3]);      // exchange complete
-            fprintf(stderr, "[sphb200 rank %d] pass %d: launches %.3f ms; exchange released at +%.3f, complete at +%.3f ms\n", slab.rank,
-                    p, pass_ms, xstart, xend);
-        }
-        for (auto &e : dbg) cudaEventDestroy(e);
+    double st[SPHB200_N_STAGES] = {0};
+    auto el = [&](cudaEvent_t a, cudaEvent_t b) -> double {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0.0; }
+        return (double)ms;
+    };
+    st[SPHB200_STAGE_TIMESTEP] = el(hev[0], hev[1]) + el(hev[2], hev[3]);
+    st[SPHB200_STAGE_ALLREDUCE] = el(hev[1], hev[2]);
+    for (int k = 0; k < 8; ++k) st[SPHB200_STAGE_REBUILD + k] = el(ev[k], ev[k + 1]);
+    for (int p = 0; p < 2; ++p) {
+        cudaEvent_t *x = xev + 4 * p;
+        const bool have_x = slab.left >= 0 || slab.right >= 0;
+        const double dur = have_x ? el(x[1], x[2]) : 0.0;
+        // exposed: how long after the interior bricks the exchange still ran
+        const double tail = have_x ? el(x[0], x[2]) - el(x[0], x[3]) : 0.0;
+        st[p ? SPHB200_STAGE_HALO2 : SPHB200_STAGE_HALO1] = dur;
+        st[p ? SPHB200_STAGE_HALO2_EXPOSED : SPHB200_STAGE_HALO1_EXPOSED] = tail > 0.0 ? tail : 0.0;
     }
-    float t[6];
-    CKS(cudaEventElapsedTime(&t[0], ev[6], ev[0]));
-    for (int k = 0; k < 5; ++k) CKS(cudaEventElapsedTime(&t[k + 1], ev[k], ev[k + 1]));
-    double out[5] = {t[0], t[1], t[2], t[4], (double)t[3] + t[5]};
-    for (int k = 0; k < 5 && k < cnt; ++k) ms_out[k] = out[k];
+    for (int k = 0; k < cnt && k < SPHB200_N_STAGES; ++k) ms_out[k] = st[k];
     for (auto &e : ev) cudaEventDestroy(e);
+    for (auto &e : xev) cudaEventDestroy(e);
+    for (auto &e : hev) cudaEventDestroy(e);
     if ((rc = sync_ctl())) return rc;
     if (h_ctl->error) return fail(h_ctl->error, "device reported error %d", h_ctl->error);
     return SPHB200_OK;

@@ -901,13 +901,19 @@ class Sim final : public sphb200_sim {
         CK(cudaGetLastError());
         return SPHB200_OK;
     }
+    // the (predicated) list build + reorder of a step; runs before pass 1
+    int enqueue_list_build() {
+        if (!lists_on()) return SPHB200_OK;
+        int rc = ensure_lists();
+        if (rc) return rc;
+        return generic ? launch_list_build<true>() : launch_list_build<false>();
+    }
     int launch_interact(int pass, int epilogue) {
         if (lists_on() && epilogue == EPI_FUSED) {
             // per pass two launches, exactly one of which does the work (ctl->list_mode[pass]): the
-            // cull kernel or the list kernel; pass 1 is preceded by the (predicated) list build
+            // cull kernel or the list kernel
             int rc = ensure_lists();
             if (rc) return rc;
-            if (pass == 0 && brick_part != 2 && (rc = generic ? launch_list_build<true>() : launch_list_build<false>())) return rc;
             if ((rc = launch_cull(pass, epilogue, 0))) return rc;
             if (generic) return pass ? launch_ring_t<1, true>(epilogue) : launch_ring_t<0, true>(epilogue);
             return pass ? launch_ring_t<1, false>(epilogue) : launch_ring_t<0, false>(epilogue);
@@ -960,19 +966,31 @@ class Sim final : public sphb200_sim {
         CK(cudaGetLastError());
         return SPHB200_OK;
     }
-    // phase B: S2 .. S19
-    int enqueue_step_body() {
+    // phase B: S2 .. S19.  ev (optional, 10 events): stage boundaries for stage_times()
+    int enqueue_step_body(cudaEvent_t *ev = nullptr) {
         int rc;
-        if ((rc = enqueue_rebuild())) return rc;
-        if ((rc = enqueue_motion(-1.0))) return rc;                       // S3
+#define EV(k) if (ev) CK(cudaEventRecord(ev[k], stream))
+        EV(0);
+        if ((rc = enqueue_rebuild())) return rc;                          // S2  "02 Calculate IndexCounter"
+        EV(1);
+        if ((rc = enqueue_motion(-1.0))) return rc;                       // S3  "Motion"
         if ((rc = enqueue_snapshots())) return rc;
-        if (prm.mdbc && (rc = enqueue_mdbc())) return rc;                 // S6
-        if ((rc = launch_interact(0, EPI_FUSED))) return rc;              // S4-S10, S13
-        if ((rc = enqueue_motion(-1.0))) return rc;                       // S12
-        if ((rc = launch_interact(1, EPI_FUSED))) return rc;              // S11, S14-S18
-        k_step_end<<<1, 1, 0, stream>>>(d_ctl.p);                         // S19
+        EV(2);
+        if (prm.mdbc && (rc = enqueue_mdbc())) return rc;                 // S6  "04 Apply MDBC before Half TimeStep"
+        EV(3);
+        if ((rc = enqueue_list_build())) return rc;                       //     neighbour-list maintenance (no reference stage)
+        EV(4);
+        if ((rc = launch_interact(0, EPI_FUSED))) return rc;              // S4-S10, S13  "05", "03", "06", "07"
+        EV(5);
+        if ((rc = enqueue_motion(-1.0))) return rc;                       // S12 "Motion"
+        EV(6);
+        if ((rc = launch_interact(1, EPI_FUSED))) return rc;              // S11, S14-S18  "08", "03", "09", "10", "11"
+        EV(7);
+        k_step_end<<<1, 1, 0, stream>>>(d_ctl.p);                         // S19 "12 Update MetaData"
         ++launches;
         CK(cudaGetLastError());
+        EV(8);
+#undef EV
         have_half = true;
         have_cells = true;
         return SPHB200_OK;
@@ -1079,11 +1097,11 @@ class Sim final : public sphb200_sim {
     int slab_exchange_counts(int to_left, int to_right, int *from_left, int *from_right);
     int slab_exchange_records(Table<T, D> from, int sl0, int nl, int sr0, int nr, int dst0, int rl, int rr);
     int slab_exchange_halo(TA *a, TB *b, cudaStream_t st);
-    int slab_pass(int pass, TA *xa, TB *xb);
+    int slab_pass(int pass, TA *xa, TB *xb, cudaEvent_t *xev = nullptr);
     int slab_allreduce_ctl();
     int slab_sort(const SlabFilter &flt, int count_rebuild);
     int slab_rebuild();
-    int slab_step_body(cudaEvent_t *ev, bool host_synced = true);
+    int slab_step_body(cudaEvent_t *ev, bool host_synced = true, cudaEvent_t *xev = nullptr);
     int slab_resume_after_pause();
     int slab_check_head(bool *stop, bool until_target);
     int slab_stage_times(double *ms_out, int cnt);
@@ -1355,38 +1373,31 @@ class Sim final : public sphb200_sim {
         return SPHB200_OK;
     }
 
-    // per-stage device times of one step (ms): reduce+control, rebuild, pass 0, pass 1 — the
-    // reference's TimerOutputs labels "01", "02", "05/06", "08-11" (src/SPHCellList.jl:748-800)
+    // per-stage device times of ONE extra step (ms), see SPHB200_STAGE_* in include/sphb200.h: the
+    // reference's TimerOutputs labels "01" .. "12" (src/SPHCellList.jl:748-800) grouped the way the fused
+    // kernels group them.  Advances the simulation by one step.
     int stage_times(double *ms_out, int cnt) override {
         if (!uploaded || !have_cells) return fail(SPHB200_ESTATE, "stage_times needs a running simulation");
+        if (!ms_out || cnt < 1) return fail(SPHB200_EINVAL, "stage_times: no output array");
         CK(cudaSetDevice(device));
+        for (int k = 0; k < cnt; ++k) ms_out[k] = 0.0;
         if (slab.active) return slab_stage_times(ms_out, cnt);
-        cudaEvent_t ev[6];
+        cudaEvent_t ev[10];
         for (auto &e : ev) CK(cudaEventCreate(&e));
         int rc = 0;
-        CK(cudaEventRecord(ev[0], stream));
+        CK(cudaEventRecord(ev[9], stream));
         if ((rc = enqueue_step_head())) return rc;
-        CK(cudaEventRecord(ev[1], stream));
-        if ((rc = enqueue_rebuild())) return rc;
-        if ((rc = enqueue_motion(-1.0))) return rc;
-        if ((rc = enqueue_snapshots())) return rc;
-        if (prm.mdbc && (rc = enqueue_mdbc())) return rc;
-        CK(cudaEventRecord(ev[2], stream));
-        if ((rc = launch_interact(0, EPI_FUSED))) return rc;
-        CK(cudaEventRecord(ev[3], stream));
-        if ((rc = enqueue_motion(-1.0))) return rc;
-        if ((rc = launch_interact(1, EPI_FUSED))) return rc;
-        CK(cudaEventRecord(ev[4], stream));
-        k_step_end<<<1, 1, 0, stream>>>(d_ctl.p);
-        ++launches;
-        CK(cudaEventRecord(ev[5], stream));
+        if ((rc = enqueue_step_body(ev))) return rc;
         CK(cudaStreamSynchronize(stream));
-        have_half = true;
-        for (int k = 0; k < 5 && k < cnt; ++k) {
-            float ms = 0.f;
+        double st[SPHB200_N_STAGES] = {0};
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ev[9], ev[0]));
+        st[SPHB200_STAGE_TIMESTEP] = ms;
+        for (int k = 0; k < 8; ++k) {
             CK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
-            ms_out[k] = ms;
+            st[SPHB200_STAGE_REBUILD + k] = ms;
         }
+        for (int k = 0; k < cnt && k < SPHB200_N_STAGES; ++k) ms_out[k] = st[k];
         for (auto &e : ev) cudaEventDestroy(e);
         if ((rc = sync_ctl())) return rc;
         if (h_ctl->error) return fail(h_ctl->error, "device reported error %d", h_ctl->error);

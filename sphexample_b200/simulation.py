@@ -18,6 +18,15 @@ from .lib import lib
 from .preprocess import SimParticles
 
 
+# order of SPHB200_STAGE_* in include/sphb200.h, with the reference's timer labels
+STAGE_NAMES = ("01 Update TimeStep (+S0/S1 reductions, control)", "02 Calculate IndexCounter (UpdateNeighbors!)",
+               "Motion (first) + state-n snapshots", "04 Apply MDBC before Half TimeStep", "neighbour-list build + reorder",
+               "05-07 First NeighborLoop + half step (fused)", "Motion (second)",
+               "08-11 Second NeighborLoop + full step (fused)", "12 Update MetaData", "slab: all-reduce (incl. wait for the slowest rank)",
+               "slab: pass-1 halo exchange", "slab: pass-1 halo exchange not hidden", "slab: pass-2 halo exchange",
+               "slab: pass-2 halo exchange not hidden", "", "")
+
+
 class SphError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"sphb200 error {code}: {msg}")
@@ -78,6 +87,14 @@ class Simulation:
     def upload_arrays(self, position, velocity, density, types, acceleration=None, group=None, ids=None):
         """Upload from caller-owned (already typed, contiguous) host arrays without conversions."""
         n = position.shape[0]
+        for name, a, dt, shape in (("position", position, self.dtype, (n, self.D)), ("velocity", velocity, self.dtype, (n, self.D)),
+                                   ("acceleration", acceleration, self.dtype, (n, self.D)), ("density", density, self.dtype, (n,)),
+                                   ("types", types, np.uint8, (n,)), ("group", group, np.uint64, (n,)), ("ids", ids, np.int64, (n,))):
+            if a is None:
+                continue
+            if a.dtype != dt or a.shape != shape or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"upload_arrays: {name} must be a C-contiguous {np.dtype(dt).name} array of shape {shape}, "
+                                 f"got {a.dtype} {a.shape} (the library reads raw memory)")
         self._ck(self._L.sphb200_upload(self._h, n, _ptr(position), _ptr(velocity), _ptr(acceleration), _ptr(density),
                                         _ptr(types), _ptr(group), _ptr(ids), None, None))
         self.N = n
@@ -149,10 +166,12 @@ class Simulation:
         self._ck(self._L.sphb200_get_stat(self._h, name.encode(), C.byref(v)))
         return float(v.value)
 
-    def stage_times(self):
-        ms = (C.c_double * 5)()
-        self._ck(self._L.sphb200_stage_times(self._h, ms, 5))
-        return list(ms)
+    def stage_times(self) -> dict:
+        """Device time (ms) of the stages of ONE extra step, keyed by the names of include/sphb200.h
+        (SPHB200_STAGE_*): the reference's "01" .. "12" timer report, src/SPHCellList.jl:748-800."""
+        ms = (C.c_double * len(STAGE_NAMES))()
+        self._ck(self._L.sphb200_stage_times(self._h, ms, len(STAGE_NAMES)))
+        return {k: float(v) for k, v in zip(STAGE_NAMES, ms) if k}
 
     @property
     def num_particles(self) -> int:
@@ -238,6 +257,8 @@ def RunSimulation(*, SimGeometry=(), SimMetaData, SimConstants, SimKernel, SimPa
     sim = Simulation(params, device)
     sim.upload(SimParticles)
     meta = SimMetaData
+    if meta.TotalTime != 0.0 or meta.Iteration != 0:      # a restart: the device clock drives ProgressMotion and the loop condition
+        sim.set_time(meta.TotalTime, meta.Iteration)
     outputs = 0
     try:
         while True:

@@ -9,8 +9,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_the_contract_line():
-    env = dict(os.environ, SPHB200_REF_BUDGET_S="3", OMP_NUM_THREADS="4")
-    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+    # OMP_NUM_THREADS=1 is what torchrun exports: the arm must use the host cores regardless
+    env = dict(os.environ, SPHB200_REF_BUDGET_S="3", OMP_NUM_THREADS="1")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--particles", "60000"],
                          capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
@@ -21,7 +23,9 @@ def test_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and d["dtype"] == "f64"
     assert "workload" in d["config"] and d["data"] == "synthetic"
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "particles" in cb["sample"]
+    assert cb["kind"] == "port" and cb["value"] == d["value"] and "particles" in cb["sample"]
+    assert cb["cores"] == len(os.sched_getaffinity(0))
+    assert d["config"]["particles"] == 60000 or abs(d["config"]["particles"] - 60000) < 5000
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
 
