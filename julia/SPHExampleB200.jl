@@ -131,9 +131,16 @@ function upload!(h::Handle, SimParticles)
     end
 end
 
-"""Read the particle table back into SimParticles in device cell order — the order the reference's
-own `sort!(Particles, by = p -> p.Cells)` leaves it in (src/SPHCellList.jl:142)."""
-function download!(h::Handle, SimParticles; order::Integer = 0)
+"""Read the particle table back into SimParticles.
+
+`order = 1` (default): ascending ID — the order `AllocateDataStructures` leaves the table in
+(`sort!(SimParticles, by = p -> p.ID)`, src/PreProcess.jl:116) and therefore the order in which the
+columns this call does NOT overwrite (GravityFactor, MotionLimiter, BoundaryBool, GhostPoints,
+GhostNormals, Kernel, KernelGradient, ChunkID) still sit on the host: every row stays one particle.
+`order = 0` returns the device's cell order (what the reference's own `sort!(Particles, by = p ->
+p.Cells)`, src/SPHCellList.jl:142, would leave behind); use it only if you also permute those
+columns yourself (download the IDs first and apply `sortperm`)."""
+function download!(h::Handle, SimParticles; order::Integer = 1)
     N  = length(SimParticles)
     D  = length(eltype(SimParticles.Position))
     id = Vector{Int64}(undef, N); ty = Vector{UInt8}(undef, N); gm = Vector{UInt64}(undef, N)

@@ -89,8 +89,7 @@ struct InteractArgs {
     int *nl_cnt;
     size_t nl_stride;
     int lcap;                          // list capacity per particle (multiple of 8)
-    int list_cap_cand;                 // candidates (incl. the 8 sentinel records) one ring slot of the list kernel holds
-    int *brick_total8;                 // per brick: window length rounded up to 8 = index of the first sentinel record
+    int list_cap_cand;                 // candidates one ring slot of the list kernel holds; its last 8 records are the sentinels
     int list_reorder;                  // 1: k_list_reorder runs after a build (bank-aware entry order, sph_listorder.h)
     T Hs2;                             // (H + skin)^2: acceptance radius of a list build
     int force_cull;                    // 1: ignore ctl->list_mode (stage-level entry points)

@@ -60,8 +60,8 @@ struct RingGeom {
     static constexpr int SMEM = NSLOT * SLOT_BYTES;
     static constexpr int NCW = SPH_RING_NCW;                        // consumer warps
     static constexpr int THREADS = (NCW + 1) * 32;
-    // a brick's window (4-aligned row spans) + 8 (rounding to 8) + 8 sentinels must fit
-    static constexpr int WINDOW_LIMIT = CAP - 16 - 6 * ((D == 3) ? 9 : 3);
+    // a brick's window (4-aligned row spans) + the 8 sentinels must fit
+    static constexpr int WINDOW_LIMIT = CAP - 8 - 6 * ((D == 3) ? 9 : 3);
 };
 
 // =================================================================================================
@@ -133,13 +133,12 @@ __global__ void __launch_bounds__(BT) k_list_build(const InteractArgs<T, D> g) {
                 o += s_len[r];
             }
             s_off[NR] = o;
-            // the list kernel stages the whole window + 8 sentinel records in one ring slot
-            if (((o + 7) & ~7) + 8 > g.list_cap_cand) atomicOr(&g.ctl->list_fail, 1);
-            g.brick_total8[bidx] = (o + 7) & ~7;
+            // the list kernel stages the whole window in one ring slot, whose last 8 records are the sentinels
+            if (o > g.list_cap_cand - 8) atomicOr(&g.ctl->list_fail, 1);
         }
         __syncthreads();
         const int total = s_off[NR];
-        const unsigned total8 = (unsigned)((total + 7) & ~7);   // padding entry = sentinel of bank group 0
+        const unsigned total8 = (unsigned)(g.list_cap_cand - 8);   // padding entry = sentinel of bank group 0 (list_sentinel_base)
 
         const int i = br.t0 + tid;
         const bool valid = i < br.t1;
@@ -296,7 +295,7 @@ constexpr int REORDER_MAX_SLOTS = 256;
 
 template <int BT>
 __global__ void __launch_bounds__(BT) k_list_reorder(Ctl *ctl, const GridInfo *grid, const Brick *__restrict__ bricks,
-                                                     const int *__restrict__ brick_total8, uint4 *nl,
+                                                     unsigned sentinel_base, uint4 *nl,
                                                      const int *__restrict__ nl_cnt, size_t nl_stride, int lcap) {
     if (ctl->error || ctl->done || !ctl->list_build || ctl->list_fail) return;
     extern __shared__ __align__(16) unsigned short s_out[];   // [REORDER_MAX_SLOTS][BT], then the overflow scratch [REORDER_OVF_CAP][BT]
@@ -311,7 +310,7 @@ __global__ void __launch_bounds__(BT) k_list_reorder(Ctl *ctl, const GridInfo *g
         const int bidx = s_brick;
         if (bidx >= nbricks) break;
         const Brick br = bricks[bidx];
-        const unsigned total8 = (unsigned)brick_total8[bidx];
+        const unsigned total8 = sentinel_base;   // window indices >= this are sentinels / padding
         for (int i = br.t0 + tid; i < br.t1; i += BT) {
             const int n_slots = min(nl_cnt[i], lcap);
             if (n_slots > REORDER_MAX_SLOTS) continue;
@@ -387,14 +386,14 @@ __global__ void __launch_bounds__(BT) k_list_reorder(Ctl *ctl, const GridInfo *g
 // a 32-target sub-brick); for every list position the 8 lanes' window indices are compared: a
 // 16-byte gather costs as many wavefronts as the largest number of DISTINCT indices in one bank
 // group (index mod 8).  out[0] += wavefronts, out[1] += quarter-warp loads, out[2] += real entries.
-__global__ void k_list_diag(const GridInfo *grid, const Brick *__restrict__ bricks, const int *__restrict__ brick_total8,
+__global__ void k_list_diag(const GridInfo *grid, const Brick *__restrict__ bricks, unsigned sentinel_base,
                             const uint4 *__restrict__ nl, const int *__restrict__ nl_cnt, size_t nl_stride,
                             unsigned long long *out) {
     const int nbricks = grid->nbricks;
     unsigned long long wf = 0, loads = 0, real = 0;
     for (int b = blockIdx.x; b < nbricks; b += gridDim.x) {
         const Brick br = bricks[b];
-        const unsigned total8 = (unsigned)brick_total8[b];
+        const unsigned total8 = sentinel_base;
         const int nq = (br.t1 - br.t0 + 7) >> 3;
         for (int qd = threadIdx.x; qd < nq; qd += blockDim.x) {
             const int i0 = br.t0 + qd * 8;
@@ -547,7 +546,7 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_full[NSLOT], s_empty[NSLOT];
-    __shared__ int s_meta[NSLOT][4];            // t0, t1, total8 (< 0: no more bricks), brick index
+    __shared__ int s_meta[NSLOT][4];            // t0, t1, window length (< 0: no more bricks), brick index
     __shared__ int s_sub[NSLOT], s_done[NSLOT];  // sub-brick ticket / finished sub-bricks of the staged brick
 
     const int tid = threadIdx.x;
@@ -564,6 +563,27 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
             s_done[s] = 0;
         }
         mbar_fence_init();
+    }
+    // The 8 sentinel records (one per bank group) are the last 8 records of every slot, written once:
+    // infinitely far away, so that the clamped kernel factor is an exact zero.  A staged window never
+    // reaches them (k_list_build checks), and the lists' padding refers to them by a fixed index.
+    const int sent_base = g.list_cap_cand - 8;
+    if (tid < 8 * NSLOT) {
+        unsigned char *const sbs = smem_raw + (size_t)(tid >> 3) * RG::SLOT_BYTES;
+        T far[D], zero[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            far[k] = T(1e15);   // finite: the branch-free pair body must not meet inf * 0
+            zero[k] = T(0);
+        }
+        TA fa;
+        TB fb;
+        L::pack(fa, fb, far, zero, T(1), T(0));
+        const int sj = sent_base + (tid & 7);
+        reinterpret_cast<TA *>(sbs)[sj] = fa;
+        reinterpret_cast<TB *>(sbs + OFF_B)[sj] = fb;
+        if (PASS) reinterpret_cast<T *>(sbs + OFF_R)[sj] = T(1);
+        if (use_sps) reinterpret_cast<TB *>(sbs + OFF_BN)[sj] = fb;
     }
     __syncthreads();
 
@@ -609,7 +629,6 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
             }
             const int total = __shfl_sync(0xffffffffu, off, NR - 1);
             off -= len;
-            const int total8 = (total + 7) & ~7;
             if (use > 0) mbar_wait(&s_empty[slot], (use - 1) & 1u);
             if (!more) {
                 if (lane == 0) {
@@ -625,30 +644,10 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
             if (lane == 0) {
                 s_meta[slot][0] = br.t0;
                 s_meta[slot][1] = br.t1;
-                s_meta[slot][2] = total8;
+                s_meta[slot][2] = total;
                 s_meta[slot][3] = bidx;
                 s_sub[slot] = 0;
                 s_done[slot] = 0;
-            }
-            if (lane < 8 + (total8 - total)) {
-                // the 8 sentinel records (one per bank group; also the rounding gap): infinitely far
-                // away, so that the clamped kernel factor is an exact zero
-                T far[D], zero[D];
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    far[k] = T(1e15);   // finite: the branch-free pair body must not meet inf * 0
-                    zero[k] = T(0);
-                }
-                TA fa;
-                TB fb;
-                L::pack(fa, fb, far, zero, T(1), T(0));
-                const int sj = total + lane;
-                if (sj < CAP) {
-                    sA[sj] = fa;
-                    sB[sj] = fb;
-                    if (PASS) sR[sj] = T(1);
-                    if (use_sps) sBn[sj] = fb;
-                }
             }
             __syncwarp();
             if (lane == 0) {
@@ -677,8 +676,7 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
         const int slot = seq % NSLOT;
         const uint32_t use = (uint32_t)(seq / NSLOT);
         mbar_wait(&s_full[slot], use & 1u);
-        const int total8 = s_meta[slot][2];
-        if (total8 < 0) break;
+        if (s_meta[slot][2] < 0) break;
         const int t0 = s_meta[slot][0], t1 = s_meta[slot][1], bidx = s_meta[slot][3];
         const int nsub = (t1 - t0 + 31) >> 5;
         const unsigned char *const sb = smem_raw + (size_t)slot * RG::SLOT_BYTES;
@@ -691,7 +689,7 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
         {
             unsigned e[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) e[u] = (unsigned)total8 + (unsigned)((lane + u) & 7);
+            for (int u = 0; u < 8; ++u) e[u] = (unsigned)sent_base + (unsigned)((lane + u) & 7);
             pad = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
         }
         for (;;) {

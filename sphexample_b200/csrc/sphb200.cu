@@ -214,7 +214,6 @@ class Sim final : public sphb200_sim {
     // cell structure
     DevBuf<int> cell_count, cell_start, scan_partial;
     DevBuf<Brick> bricks;
-    DevBuf<int> brick_total8;   // per brick: sentinel base of its candidate window (k_list_build -> k_list_reorder)
     // cudaFuncSetAttribute / occupancy results are per device and per handle: kernel -> {dynamic smem, CTAs per SM}
     std::map<const void *, std::pair<int, int>> kernel_cfg;
     long long cell_cap = 0, row_cap = 0;
@@ -363,7 +362,7 @@ class Sim final : public sphb200_sim {
             DevBuf<unsigned long long> acc3;
             CK(acc3.alloc(3));
             CK(cudaMemsetAsync(acc3.p, 0, 24, stream));
-            k_list_diag<<<num_sms * 4, 128, 0, stream>>>(d_grid.p, bricks.p, brick_total8.p, nl.p, nl_cnt.p, nl_stride, acc3.p);
+            k_list_diag<<<num_sms * 4, 128, 0, stream>>>(d_grid.p, bricks.p, (unsigned)(list_cap_cand() - 8), nl.p, nl_cnt.p, nl_stride, acc3.p);
             ++launches;
             unsigned long long h3[3];
             CK(cudaMemcpyAsync(h3, acc3.p, 24, cudaMemcpyDeviceToHost, stream));
@@ -448,7 +447,6 @@ class Sim final : public sphb200_sim {
         row_cap = cap / 3 + 1;
         brick_cap = (int)std::min<long long>((long long)(n_alloc / 8) + row_cap + 16, INT_MAX);
         CK(bricks.alloc((size_t)brick_cap));
-        CK(brick_total8.alloc((size_t)brick_cap));
         return SPHB200_OK;
     }
 
@@ -743,13 +741,13 @@ class Sim final : public sphb200_sim {
             const int per = generic ? RingGeom<T, D, true>::S1::per_candidate : RingGeom<T, D, false>::S1::per_candidate;
             cap = std::min(cap, ((opt_list_smem_kb * 1024 - 64) / per) & ~7);
         }
-        return cap;
+        return std::max(cap, 16);   // (its last 8 records are the sentinels)
     }
     // candidates a brick's window may hold: what the list kernel can stage, else a bound that merely
     // keeps sparse rows from producing row-long windows
     int brick_window_limit() {
         if (!lists_on()) return 8192;
-        const int lim = list_cap_cand() - 16 - 6 * ((D == 3) ? 9 : 3);   // RingGeom::WINDOW_LIMIT for the effective cap
+        const int lim = list_cap_cand() - 8 - 6 * ((D == 3) ? 9 : 3);   // RingGeom::WINDOW_LIMIT for the effective cap
         return lim >= 64 ? lim : 64;
     }
     double motion_vmax() const {
@@ -809,7 +807,6 @@ class Sim final : public sphb200_sim {
         g.nl_stride = nl_stride;
         g.lcap = opt_lcap;
         g.list_cap_cand = list_cap_cand();
-        g.brick_total8 = brick_total8.p;
         g.list_reorder = opt_list_reorder;
         const double Hs = prm.H * (1.0 + opt_skin);
         g.Hs2 = (T)(Hs * Hs);
@@ -873,8 +870,8 @@ class Sim final : public sphb200_sim {
             auto rk = k_list_reorder<BT>;
             const int rsmem = (REORDER_MAX_SLOTS + REORDER_OVF_CAP) * BT * 2;
             if ((rc = configure_kernel(rk, BT, rsmem, &ctas))) return rc;
-            rk<<<persistent_blocks(ctas), BT, rsmem, stream>>>(d_ctl.p, d_grid.p, bricks.p, brick_total8.p, nl.p, nl_cnt.p, nl_stride,
-                                                             opt_lcap);
+            rk<<<persistent_blocks(ctas), BT, rsmem, stream>>>(d_ctl.p, d_grid.p, bricks.p, (unsigned)(list_cap_cand() - 8), nl.p, nl_cnt.p,
+                                                             nl_stride, opt_lcap);
             ++launches;
             CK(cudaGetLastError());
         }

@@ -38,3 +38,6 @@ if __name__ == "__main__":
     save("still_wedge_mdbc_dp0.02.npz", sw)
     save("dam_break_3d_dp0.02.npz", AllocateDataStructures(
         geom("dam_break_3d/DamBreak3d_Dp0.02_Bound.csv", "dam_break_3d/DamBreak3d_Dp0.02_Fluid.csv"), 3))
+    # the exact upstream 3D case (example/Dambreak3d.jl: dx = 0.0085, N = 171 496)
+    save("dam_break_3d_dp0.0085.npz", AllocateDataStructures(
+        geom("dam_break_3d/DamBreak3d_Dp0.0085_Bound.csv", "dam_break_3d/DamBreak3d_Dp0.0085_Fluid.csv"), 3))

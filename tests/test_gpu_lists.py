@@ -26,7 +26,7 @@ def run(case, steps, **opts):
 
 @pytest.mark.parametrize("name,steps,vel,tol", [
     ("c1_2d_f64", 120, 0.5, 1e-11), ("c1_2d_f64", 200, 3.0, 1e-10),
-    ("c1_2d_f32", 120, 0.5, 2e-4), ("3d_f32", 80, 0.5, 2e-4), ("3d_f32", 150, 3.0, 1e-3),
+    ("c1_2d_f32", 120, 0.5, 6e-5), ("3d_f32", 80, 0.5, 1e-5), ("3d_f32", 150, 3.0, 4e-5),   # measured 2.2e-5, 2.6e-6, 1.3e-5
 ])
 def test_lists_match_cull_path(name, steps, vel, tol):
     mk = {"c1_2d_f64": lambda: util.case_c1("float64"), "c1_2d_f32": lambda: util.case_c1("float32"),
@@ -78,7 +78,7 @@ def test_overflowing_build_falls_back_to_the_cull_kernel():
     assert st2["off"] == 1
     for s in (s1, s2):
         for f in ("Position", "Velocity", "Density"):
-            assert np.array_equal(s[f], s0[f]) or util.relerr(s[f], s0[f]) < 2e-4, f
+            assert np.array_equal(s[f], s0[f]) or util.relerr(s[f], s0[f]) < 1e-5, f
 
 
 def test_stage_level_calls_void_the_lists(oracle_lib):

@@ -1,8 +1,11 @@
 """GPU parity tests: libsphb200.so (through the C-ABI) against the CPU oracle on the same inputs.
 
-Tolerances, relative to max|field|:
-  one interaction pass   fp64 1e-12   fp32 2e-4 (x_a - x_b cancellation at dp/|x| ~ 1e-2)
-  after 100 steps        fp64 1e-8    fp32 stated per test
+Tolerances, relative to max|field| (fp64 1e-12 per pass / 1e-8 after 100 steps; fp32
+1e-5 per pass / 1e-3 after 100 steps).  The fp32 tolerances below are <= 3x the margin measured on
+B200 (profiles/r2l_parity.txt): dρ/dt of one pass 6.6e-7, acceleration 1.3e-5 — slightly ABOVE the
+survey's 1e-5 because x_a - x_b of two fp32 positions at |x| ~ 1 m carries an absolute error of
+~1e-7 m against pair distances of ~1e-2 m (1e-5 relative); the MUFU approximations of the fast pair
+body are 1-2 ulp and do not show.  After 60-100 steps: velocity 8e-6 .. 1.5e-4, density <= 6e-6.
 Integer / index work (cell coordinates, cell ranges, the sort permutation) is bit-exact.
 """
 import numpy as np
@@ -14,7 +17,8 @@ from sphexample_b200.simulation import Simulation, SphError
 
 pytestmark = pytest.mark.gpu
 
-TOL_PASS = {"float64": 1e-12, "float32": 2e-4}
+TOL_PASS = {"float64": 1e-12, "float32": 4e-5}      # acceleration; dρ/dt: TOL_PASS_DRHO
+TOL_PASS_DRHO = {"float64": 1e-12, "float32": 2e-6}
 
 
 def make(case, oracle_lib, geometry=(), tweak=None, options=None, nthreads=4):
@@ -75,9 +79,8 @@ def test_neighbor_loop_pass0(oracle_lib, name, compact, tma):
     orc.pressure(0)
     d, a = sim.NeighborLoop(0)
     orc.neighbor_loop(0)
-    tol = TOL_PASS[case.meta.FloatType]
-    util.check(util.relerr(d, orc.get("drhodt")), tol)
-    util.check(util.relerr(a, orc.get("acc")), tol)
+    util.check(util.relerr(d, orc.get("drhodt")), TOL_PASS_DRHO[case.meta.FloatType])
+    util.check(util.relerr(a, orc.get("acc")), TOL_PASS[case.meta.FloatType])
     sim.close()
 
 
@@ -95,19 +98,19 @@ def test_staged_step_matches_oracle(oracle_lib, name):
     sim.HalfTimeStep(dt / 2); orc.half_time_step(dt / 2)
     half = sim.download_half()
     util.check(util.relerr(half["Position"], orc.get("pos_h")), (1e-7 if f32 else 1e-15))
-    util.check(util.relerr(half["Velocity"], orc.get("vel_h")), tol)
-    util.check(util.relerr(half["Density"], orc.get("rho_h")), (1e-6 if f32 else 1e-14))
+    util.check(util.relerr(half["Velocity"], orc.get("vel_h")), (1e-6 if f32 else tol))       # measured 2.4e-7
+    util.check(util.relerr(half["Density"], orc.get("rho_h")), (1e-7 if f32 else 1e-14))      # measured 3.0e-8
     sim.Pressure(1); orc.pressure(1)
     d, a = sim.NeighborLoop(1)
     orc.neighbor_loop(1)
-    util.check(util.relerr(d, orc.get("drhodt")), tol)
-    util.check(util.relerr(a, orc.get("acc")), tol)
+    util.check(util.relerr(d, orc.get("drhodt")), (4e-6 if f32 else tol))                      # measured 1.3e-6
+    util.check(util.relerr(a, orc.get("acc")), (5e-5 if f32 else tol))                         # measured 1.8e-5
     sim.FullTimeStep(dt); orc.full_time_step(dt)
     st = sim.download()
     util.check(util.relerr(st["Position"], orc.get("pos")), (1e-7 if f32 else 1e-15))
-    util.check(util.relerr(st["Velocity"], orc.get("vel")), tol)
-    util.check(util.relerr(st["Density"], orc.get("rho")), (1e-6 if f32 else 1e-14))
-    util.check(util.relerr(st["Acceleration"], orc.get("acc")), tol)
+    util.check(util.relerr(st["Velocity"], orc.get("vel")), (2e-6 if f32 else tol))            # measured 5.8e-7
+    util.check(util.relerr(st["Density"], orc.get("rho")), (5e-7 if f32 else 1e-14))           # measured 1.5e-7
+    util.check(util.relerr(st["Acceleration"], orc.get("acc")), (5e-5 if f32 else tol))        # measured 1.8e-5
     sim.close()
 
 
@@ -197,7 +200,7 @@ def test_model_variants_match_oracle(oracle_lib, name, model):
 @pytest.mark.parametrize("name,nsteps,tol_v,tol_r", [
     ("c1_2d_f64", 1, 1e-12, 1e-14), ("c1_2d_f64", 10, 1e-10, 1e-12), ("c1_2d_f64", 100, 1e-8, 1e-10),
     ("3d_f64", 10, 1e-10, 1e-12), ("3d_f64", 60, 1e-8, 1e-10),
-    ("c1_2d_f32", 100, 5e-3, 1e-5), ("3d_f32", 60, 5e-3, 1e-5),
+    ("c1_2d_f32", 100, 4e-4, 1.5e-5), ("3d_f32", 60, 2.5e-5, 8e-6),     # measured 1.5e-4 / 5.8e-6 and 8.4e-6 / 2.8e-6
 ])
 def test_fused_steps_match_oracle(oracle_lib, name, nsteps, tol_v, tol_r):
     case = CASES[name]()
@@ -214,10 +217,10 @@ def test_fused_steps_match_oracle(oracle_lib, name, nsteps, tol_v, tol_r):
     st = sim.download(order="id")
     ids = orc.ids
     assert np.array_equal(st["ID"], np.sort(ids))
-    util.check(util.relerr(st["Position"], util.by_id(ids, orc.get("pos"))), (2e-6 if f32 else 1e-12))
+    util.check(util.relerr(st["Position"], util.by_id(ids, orc.get("pos"))), (1e-6 if f32 else 1e-12))      # measured 3.5e-7
     util.check(util.relerr(st["Velocity"], util.by_id(ids, orc.get("vel"))), tol_v)
     util.check(util.relerr(st["Density"], util.by_id(ids, orc.get("rho"))), tol_r)
-    util.check(util.relerr(st["Pressure"], util.by_id(ids, np.asarray(_press(p, orc.get("rho"))))), (1e-2 if f32 else 1e-8))
+    util.check(util.relerr(st["Pressure"], util.by_id(ids, np.asarray(_press(p, orc.get("rho"))))), (2e-3 if f32 else 1e-8))   # measured 6.9e-4 (2D), 7.5e-5 (3D)
     sim.close()
 
 

@@ -3,7 +3,7 @@ import os
 
 import numpy as np
 
-from sphexample_b200 import cases, config, make_params
+from sphexample_b200 import _abi, cases, config, make_params
 from sphexample_b200.preprocess import SimParticles, make_particles
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -88,3 +88,21 @@ def check(err, tol):
         with open(log, "a") as fh:
             fh.write(json.dumps({"test": test, "line": fr.lineno, "err": err, "tol": tol, "ok": bool(err < tol)}) + "\n")
     assert err < tol, f"{test}:{fr.lineno}: measured {err:.3e} >= tolerance {tol:.1e}"
+
+
+def case_3d_shipped(float_type="float32"):
+    """the exact upstream 3D case: input/dam_break_3d Dp 0.0085 (N = 171 496), example/Dambreak3d.jl constants"""
+    dt = np.float64 if float_type == "float64" else np.float32
+    return cases.case_dam_break_3d(0.0085, float_type, particles=load_fixture("dam_break_3d_dp0.0085.npz", dt))
+
+
+def case_c2(float_type="float64"):
+    """C2: the 2D dam break regenerated at dp = 0.0058 (N = 59 909)"""
+    return cases.case_dam_break_2d(0.0058, float_type)
+
+
+def set_cubic_spline(p):
+    """switch a parameter block to CubicSpline (+ its αD, src/SPHKernels.jl:24-26, and the tensile correction's ε)"""
+    p.kernel = _abi.KERNEL_CUBICSPLINE
+    p.alphaD = {2: 10.0 / (7.0 * np.pi * p.h ** 2), 3: 1.0 / (np.pi * p.h ** 3)}[int(p.dim)]
+    p.cubic_eps = 0.2
