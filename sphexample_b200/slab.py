@@ -21,29 +21,44 @@ def cell_coord(x: np.ndarray, H_inv: float) -> np.ndarray:
     return (np.sign(x) * np.trunc(np.abs(x) * H_inv + 0.5)).astype(np.int64)
 
 
-def plan_edges(coords: np.ndarray, world: int, min_width: int = 2) -> List[int]:
+def plan_edges(coords: np.ndarray, world: int, min_width: int = 2, weights: Optional[np.ndarray] = None) -> List[int]:
     """Slab edges e[0] < e[1] < ... < e[world] on cell-layer boundaries; rank r owns layers
-    e[r] <= c < e[r+1].  Edges follow the particle-count prefix sum over layers (equal-width
-    slabs are unusable for a dam break: the water starts in one corner of the tank), subject to
-    every slab being at least `min_width` layers wide (the exchange protocol needs 2)."""
+    e[r] <= c < e[r+1].  The layers are cut into `world` contiguous groups such that the LARGEST
+    group load is as small as possible (the step time is the slowest rank's): equal-width slabs
+    are unusable for a dam break (the water starts in one corner of the tank), and rounding each
+    particle-count quantile to the nearest layer boundary — the obvious choice — can leave a rank a
+    whole layer (7 % at 14 layers per rank) above the mean.  `weights` (per particle, default 1)
+    lets cheap particles count less (a wall particle has a fraction of a fluid particle's neighbours).
+    Every slab is at least `min_width` layers wide (the exchange protocol needs 2)."""
     coords = np.asarray(coords, np.int64)
     cmin, cmax = int(coords.min()), int(coords.max())
     nlay = cmax - cmin + 1
     if nlay < world * min_width:
         raise ValueError(f"{nlay} cell layers along the slab axis cannot feed {world} ranks of >= {min_width} layers")
-    hist = np.bincount(coords - cmin, minlength=nlay)
-    cum = np.concatenate([[0], np.cumsum(hist)])          # cum[k] = particles in layers < k
-    total = cum[-1]
-    edges = [0]
-    for r in range(1, world):
-        k = int(np.searchsorted(cum, total * r / world, side="left"))
-        # choose the closer of the two layer boundaries around the quantile
-        if k > 0 and abs(cum[k - 1] - total * r / world) <= abs(cum[min(k, nlay)] - total * r / world):
-            k -= 1
-        k = max(k, edges[-1] + min_width)
-        k = min(k, nlay - (world - r) * min_width)
+    hist = np.bincount(coords - cmin, weights=None if weights is None else np.asarray(weights, np.float64), minlength=nlay)
+    cum = np.concatenate([[0.0], np.cumsum(hist, dtype=np.float64)])   # cum[k] = load of layers < k
+    load = lambda i, j: cum[j] - cum[i]
+    # best[r][k]: smallest achievable maximum load when the first k layers feed r ranks (linear partition DP)
+    INF = float("inf")
+    best = np.full((world + 1, nlay + 1), INF)
+    cut = np.zeros((world + 1, nlay + 1), np.int64)
+    best[0][0] = 0.0
+    for r in range(1, world + 1):
+        for k in range(r * min_width, nlay - (world - r) * min_width + 1):
+            lo, hi = (r - 1) * min_width, k - min_width
+            if r == 1:
+                lo = hi = 0
+            j = np.arange(lo, hi + 1)
+            cand = np.maximum(best[r - 1][lo:hi + 1], cum[k] - cum[j])
+            m = int(np.argmin(cand))
+            best[r][k], cut[r][k] = cand[m], j[m]
+    edges = [nlay]
+    k = nlay
+    for r in range(world, 0, -1):
+        k = int(cut[r][k])
         edges.append(k)
-    edges.append(nlay)
+    edges = edges[::-1]
+    assert edges[0] == 0 and all(b - a >= min_width for a, b in zip(edges, edges[1:])), edges
     return [cmin + e for e in edges]
 
 
@@ -82,12 +97,14 @@ class SlabDecomposition:
     """
 
     def __init__(self, sim, particles, H_inv: float, rank: int, world: int, axis: Optional[int] = None,
-                 edges: Optional[Sequence[int]] = None):
+                 edges: Optional[Sequence[int]] = None, boundary_weight: float = 1.0):
         self.sim, self.parts, self.H_inv, self.rank, self.world = sim, particles, float(H_inv), rank, world
         pos = np.asarray(particles.Position)
         self.axis = best_axis(pos, self.H_inv, world) if axis is None else int(axis)
         self.coords = cell_coord(pos[:, self.axis], self.H_inv)
-        self.edges = list(edges) if edges is not None else plan_edges(self.coords, world)
+        self.boundary_weight = float(boundary_weight)
+        w = None if boundary_weight == 1.0 else np.where(np.asarray(particles.Type) == 1, 1.0, self.boundary_weight)
+        self.edges = list(edges) if edges is not None else plan_edges(self.coords, world, weights=w)
         self.mine = np.nonzero(owner_of(self.coords, self.edges) == rank)[0]
         self.n_owned = int(self.mine.size)
 
@@ -141,7 +158,8 @@ class SlabDecomposition:
         dist.all_gather_object(parts, st)
         cat = {k: np.concatenate([p[k] for p in parts]) for k in st}
         coords = cell_coord(cat["Position"][:, self.axis], self.H_inv)
-        self.edges = plan_edges(coords, self.world)
+        w = None if self.boundary_weight == 1.0 else np.where(cat["Type"] == 1, 1.0, self.boundary_weight)
+        self.edges = plan_edges(coords, self.world, weights=w)
         mine = np.nonzero(owner_of(coords, self.edges) == self.rank)[0]
         mine = mine[np.argsort(cat["ID"][mine], kind="stable")]          # the table is kept in ascending ID order
         sub = make_particles(cat["Position"][mine], cat["Density"][mine], cat["Type"][mine], cat["GroupMarker"][mine],
