@@ -47,7 +47,15 @@ struct Ctl {
     int n_list_builds;
     double list_move;          // bound on any particle's displacement since the last list build
     double list_prev_vmax;     // max |v| at the previous step head
+    // per-brick ("local") list maintenance, see brick_list_decision below
+    int vbox_cur;              // which of the two per-cell velocity-box buffers holds the head-of-step velocities
+    int bricks_flagged;        // bricks whose lists are rebuilt in this step
+    double list_build_equiv;   // builds so far in units of "all bricks once" (what sphb200_get_stat("list_builds") reports)
+    double vmax_now;           // max |v| at this step head (incl. moving bodies)
+    long long list_missing;    // test hook (option verify_lists): pairs within H found missing from a list in use
 };
+
+enum { LIST_BUILD_NONE = 0, LIST_BUILD_ALL = 1, LIST_BUILD_FLAGGED = 2 };   // Ctl::list_build
 
 struct GridInfo {
     int bb_min[3], bb_max[3];  // bounding box of occupied reference cells (inclusive)
@@ -91,8 +99,11 @@ SPH_HD double ctl_bits_to_double(unsigned long long b) {
 // do_rebuild also raises `done`: this step's body and every later enqueued step run empty until the
 // host has rebuilt and resumes the open step — steps can be enqueued in batches without a per-step
 // host round trip and without ever running a step on stale cells.
+// list_local: the validity of the lists is tracked per brick (brick_list_decision, k_brick_bounds)
+// instead of globally: every step is a LIST_BUILD_FLAGGED build of the bricks that need one.
 template <class T>
-SPH_HD void step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, double list_skin, double motion_vmax, int pause_on_rebuild) {
+SPH_HD void step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, double list_skin, double motion_vmax, int pause_on_rebuild,
+                         int list_local = 0) {
     if (ctl->red_err && !ctl->error) ctl->error = -(int)ctl->red_err;   // slab mode: another rank failed
     ctl->red_err = 0ull;
     if (ctl->error) return;
@@ -138,6 +149,7 @@ SPH_HD void step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, double list
     // ---- which kernel serves the two passes of this step ---------------------------------------
     ctl->list_mode[0] = ctl->list_mode[1] = 0;   // LM_CULL
     ctl->list_build = 0;
+    ctl->vmax_now = vmax;
     if (list_skin > 0.0) {
         if (ctl->list_fail) {          // the last build overflowed: no lists until the cells change
             ctl->list_fail_last = ctl->list_fail;
@@ -153,7 +165,15 @@ SPH_HD void step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, double list
         const double half = ctl->dt2 * vmax;
         ctl->list_move += ctl->current_dt * fmax(ctl->list_prev_vmax, vmax);   // the step just completed
         ctl->list_prev_vmax = vmax;
-        if (!ctl->list_off) {
+        if (!ctl->list_off && list_local) {
+            // local mode: lists exist for the current cells -> only the bricks whose own displacement bound
+            // is used up are rebuilt (k_brick_bounds decides, k_list_build skips the others)
+            ctl->list_build = ctl->list_valid ? LIST_BUILD_FLAGGED : LIST_BUILD_ALL;
+            ctl->list_valid = 1;
+            ctl->list_mode[0] = 2;                                  // LM_USE
+            ctl->list_mode[1] = (half <= margin) ? 2 : 0;           // (implies every brick's own half-step test)
+            ctl->list_move = 0.0;
+        } else if (!ctl->list_off) {
             if (ctl->list_valid && ctl->list_move + half <= margin) {
                 ctl->list_mode[0] = ctl->list_mode[1] = 2;          // LM_USE
             } else {
@@ -163,6 +183,7 @@ SPH_HD void step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, double list
                 ctl->list_move = 0.0;
                 ctl->list_valid = 1;
                 ctl->n_list_builds += 1;
+                ctl->list_build_equiv += 1.0;
             }
         }
     }
@@ -177,6 +198,26 @@ SPH_HD void step_end(Ctl *ctl) {
     ctl->total_time += ctl->dt;
     ctl->step_open = 0;
     ctl->red_ready = 1;   // the fused corrector of pass 2 has accumulated the Δt / Δx reductions of the new state
+    ctl->vbox_cur ^= 1;   // k_cell_vbox of the next step head writes the other buffer
+}
+
+// Per-brick list validity.  A pair (a, b) of a brick's window that is NOT in a's list was farther
+// apart than H + skin when the list was built; it is missed only if the two have approached by more
+// than skin since.  Over one step the relative displacement of a and b is
+//   dt ((v_a + v_a')/2 - (v_b + v_b')/2),  at most  dt max(|v_a - v_b|, |v_a' - v_b'|)  <=  dt D,
+// with D the diagonal of the bounding box of all velocities in the window at the two step heads (the
+// boxes are kept per cell, k_cell_vbox) — a bound on RELATIVE velocities, so a water column that
+// moves as a whole keeps its lists; the global rule of step_control (2 dt max|v|) cannot see that.
+// `move`: accumulated bound through the previous step; the half step of pass 2 adds dt2 D.
+// Returns true when the brick's lists must be rebuilt now (and resets the bound).
+SPH_HD bool brick_list_decision(float *move, float D, double dt_prev, double dt2, double skin) {
+    const float m = *move + (float)dt_prev * D * 1.0001f;   // (rounding of the accumulation never shortens the bound)
+    if ((double)m + dt2 * (double)D > 0.98 * skin) {
+        *move = 0.f;
+        return true;
+    }
+    *move = m;
+    return false;
 }
 
 }  // namespace sph

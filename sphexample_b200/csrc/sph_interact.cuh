@@ -91,6 +91,7 @@ struct InteractArgs {
     int lcap;                          // list capacity per particle (multiple of 8)
     int list_cap_cand;                 // candidates one ring slot of the list kernel holds; its last 8 records are the sentinels
     int list_reorder;                  // 1: k_list_reorder runs after a build (bank-aware entry order, sph_listorder.h)
+    const int *brick_flag;             // per brick: rebuild its lists in this step (LIST_BUILD_FLAGGED, k_brick_bounds)
     T Hs2;                             // (H + skin)^2: acceptance radius of a list build
     int force_cull;                    // 1: ignore ctl->list_mode (stage-level entry points)
 };

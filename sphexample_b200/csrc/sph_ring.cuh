@@ -65,6 +65,107 @@ struct RingGeom {
 };
 
 // =================================================================================================
+// Per-brick list maintenance (brick_list_decision, sph_control.h).
+//   k_cell_vbox     bounding box of the velocities of every cell's particles at this step head
+//                   (owned and halo particles alike; 6 floats per cell, rounded outward), into the
+//                   buffer ctl->vbox_cur — the other buffer still holds the previous head's boxes;
+//   k_brick_bounds  per brick: the diagonal D of the union of both heads' boxes over the brick's
+//                   window cells bounds every relative velocity in the window; the brick's
+//                   accumulated relative-displacement bound decides whether its lists are rebuilt now.
+// Both run every step while lists are in use (~15 us at 1 M particles); k_list_build / k_list_reorder
+// then skip the bricks that are not flagged.
+// =================================================================================================
+template <class T, int D>
+__global__ void k_cell_vbox(const typename Lay<T, D>::TB *__restrict__ B, const int *__restrict__ cell_start, const GridInfo *grid,
+                            const Ctl *ctl, float *__restrict__ vbox, size_t buf_stride) {
+    if (ctl->error || ctl->done || ctl->list_build == LIST_BUILD_NONE) return;
+    float *const out = vbox + (size_t)ctl->vbox_cur * buf_stride;
+    const int ncell = grid->ncell;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += gridDim.x * blockDim.x) {
+        const int s = cell_start[c], e = cell_start[c + 1];
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int j = s; j < e; ++j) {
+            T v[D];
+            Lay<T, D>::vel(B[j], v);
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const float vd = sizeof(T) == 8 ? __double2float_rd((double)v[k]) : (float)v[k];
+                const float vu = sizeof(T) == 8 ? __double2float_ru((double)v[k]) : (float)v[k];
+                lo[k] = fminf(lo[k], vd);
+                hi[k] = fmaxf(hi[k], vu);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            out[(size_t)c * 6 + k] = lo[k];
+            out[(size_t)c * 6 + 3 + k] = hi[k];
+        }
+    }
+}
+
+// one WARP per brick: the lanes share the window's cells (a thread per brick spent 0.4 ms in ~750 dependent loads)
+template <int D>
+__global__ void k_brick_bounds(Ctl *ctl, const GridInfo *grid, const Brick *__restrict__ bricks, const int *__restrict__ ckey,
+                               const float *__restrict__ vbox, size_t buf_stride, float *__restrict__ brick_move,
+                               int *__restrict__ brick_flag, double skin) {
+    if (ctl->error || ctl->done || ctl->list_build == LIST_BUILD_NONE) return;
+    constexpr int NR = (D == 3) ? 9 : 3;
+    const int nbricks = grid->nbricks, nx = grid->nx, nm = grid->nm;
+    const bool all = ctl->list_build == LIST_BUILD_ALL;
+    const float vcap = 2.0f * (float)ctl->vmax_now * 1.0001f;   // no two particles differ by more than 2 max|v|
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    int flagged = 0;
+    for (int b = warp; b < nbricks; b += nwarps) {
+        float move = 0.f;
+        bool flag = true;
+        if (!all) {
+            const Brick br = bricks[b];
+            const int key0 = ckey[br.t0], key1 = ckey[br.t1 - 1];
+            const int cx0 = key0 % nx, cx1 = key1 % nx;
+            const int rowbase = key0 - cx0;
+            const int ncx = cx1 - cx0 + 3;               // cells cx0-1 .. cx1+1 of every row
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int q = lane; q < NR * ncx; q += 32) {
+                const int r = q / ncx, cx = cx0 - 1 + (q - r * ncx);
+                const int dm = (D == 3) ? (r % 3 - 1) : 0;
+                const int ds = (D == 3) ? (r / 3 - 1) : (r - 1);
+                const size_t cell = (size_t)(rowbase + (ds * nm + dm) * nx + cx);
+#pragma unroll
+                for (int buf = 0; buf < 2; ++buf) {
+                    const float *bx = vbox + (size_t)buf * buf_stride + cell * 6;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        lo[k] = fminf(lo[k], bx[k]);
+                        hi[k] = fmaxf(hi[k], bx[3 + k]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                lo[k] = warp_min(lo[k]);
+                hi[k] = warp_max(hi[k]);
+            }
+            float d2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const float w = hi[k] >= lo[k] ? (hi[k] - lo[k]) : 0.f;
+                d2 += w * w;
+            }
+            const float Dd = fminf(sqrtf(d2) * 1.0001f, vcap);
+            move = brick_move[b];
+            flag = brick_list_decision(&move, Dd, ctl->current_dt, ctl->dt2, skin);
+        }
+        if (lane == 0) {
+            brick_move[b] = move;
+            brick_flag[b] = flag ? 1 : 0;
+            flagged += flag ? 1 : 0;
+        }
+    }
+    if (lane == 0 && flagged) atomicAdd(&ctl->bricks_flagged, flagged);
+}
+
+// =================================================================================================
 // List build: the cull walk of k_interact without any physics.  Stages POSITIONS only, applies the
 // reference's stale-cell window test and r² <= (H + skin)², and appends (window index | role) to
 // the particle's list in global memory.  Runs when k_step_control raises ctl->list_build, on the
@@ -102,12 +203,17 @@ __global__ void __launch_bounds__(BT) k_list_build(const InteractArgs<T, D> g) {
     const int nbricks = g.grid->nbricks;
     const int npad = (g.grid->n_total + 3) & ~3;
     const T Hs2 = g.Hs2;
+    const bool flagged_only = g.ctl->list_build == LIST_BUILD_FLAGGED;
 
     for (;;) {
         if (tid == 0) s_brick = atomicAdd(&g.ctl->work_counter[6], 1);
         __syncthreads();
         const int bidx = s_brick;
         if (bidx >= nbricks) break;
+        if (flagged_only && !g.brick_flag[bidx]) {   // this brick's lists are still good (k_brick_bounds)
+            __syncthreads();                         // (s_brick is rewritten at the top of the loop)
+            continue;
+        }
         const Brick br = g.bricks[bidx];
         const int key0 = g.ckey[br.t0], key1 = g.ckey[br.t1 - 1];
         const int cx0 = key0 % nx, cx1 = key1 % nx;
@@ -291,13 +397,14 @@ __global__ void __launch_bounds__(BT) k_list_build(const InteractArgs<T, D> g) {
 // over-full bank groups, stay as built (valid, only slower).  Runs right after k_list_build.
 // =================================================================================================
 constexpr int REORDER_OVF_CAP = 32;
-constexpr int REORDER_MAX_SLOTS = 256;
+constexpr int REORDER_MAX_SLOTS = 288;
 
 template <int BT>
 __global__ void __launch_bounds__(BT) k_list_reorder(Ctl *ctl, const GridInfo *grid, const Brick *__restrict__ bricks,
-                                                     unsigned sentinel_base, uint4 *nl,
+                                                     const int *__restrict__ brick_flag, unsigned sentinel_base, uint4 *nl,
                                                      const int *__restrict__ nl_cnt, size_t nl_stride, int lcap) {
     if (ctl->error || ctl->done || !ctl->list_build || ctl->list_fail) return;
+    const bool flagged_only = ctl->list_build == LIST_BUILD_FLAGGED;
     extern __shared__ __align__(16) unsigned short s_out[];   // [REORDER_MAX_SLOTS][BT], then the overflow scratch [REORDER_OVF_CAP][BT]
     unsigned short *const s_ovf = s_out + (size_t)REORDER_MAX_SLOTS * BT;
     __shared__ int s_brick;
@@ -309,6 +416,7 @@ __global__ void __launch_bounds__(BT) k_list_reorder(Ctl *ctl, const GridInfo *g
         __syncthreads();
         const int bidx = s_brick;
         if (bidx >= nbricks) break;
+        if (flagged_only && !brick_flag[bidx]) continue;   // (the barrier at the top of the loop protects s_brick)
         const Brick br = bricks[bidx];
         const unsigned total8 = sentinel_base;   // window indices >= this are sentinels / padding
         for (int i = br.t0 + tid; i < br.t1; i += BT) {
@@ -379,6 +487,82 @@ __global__ void __launch_bounds__(BT) k_list_reorder(Ctl *ctl, const GridInfo *g
             }
         }
     }
+}
+
+// Test hook (option verify_lists): for every particle of every brick, every candidate of its own
+// (stale-cell) window that lies within H at the positions of the pass about to run must be in the
+// particle's list.  Brute force over global memory; counts the misses into ctl->list_missing.  This
+// is the on-device proof that the per-brick displacement bounds never let a list go stale.
+template <class T, int D, bool GENERIC, int BT>
+__global__ void __launch_bounds__(BT) k_list_verify(const InteractArgs<T, D> g, int pass) {
+    using L = Lay<T, D>;
+    constexpr int NR = (D == 3) ? 9 : 3;
+    if (g.ctl->error || g.ctl->done || g.ctl->list_fail || g.ctl->list_mode[pass] != LM_USE) return;
+    __shared__ int s_w0a[NR], s_len[NR], s_off[NR + 1];
+    const int tid = threadIdx.x;
+    const int nx = g.grid->nx, nm = g.grid->nm, nbricks = g.grid->nbricks;
+    const int npad = (g.grid->n_total + 3) & ~3;
+    long long missing = 0;
+    for (int bidx = blockIdx.x; bidx < nbricks; bidx += gridDim.x) {
+        const Brick br = g.bricks[bidx];
+        const int key0 = g.ckey[br.t0], key1 = g.ckey[br.t1 - 1];
+        const int cx0 = key0 % nx, cx1 = key1 % nx;
+        const int rowbase = key0 - cx0;
+        __syncthreads();
+        if (tid < NR) {
+            int dm = (D == 3) ? (tid % 3 - 1) : 0;
+            int ds = (D == 3) ? (tid / 3 - 1) : (tid - 1);
+            int rk = rowbase + (ds * nm + dm) * nx;
+            int w0 = g.cell_start[rk + cx0 - 1];
+            int w1 = g.cell_start[rk + cx1 + 2];
+            int w0a = w0 & ~3;
+            int w1a = min((w1 + 3) & ~3, npad);
+            if (w1 <= w0) w1a = w0a;
+            s_w0a[tid] = w0a;
+            s_len[tid] = w1a - w0a;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int o = 0;
+            for (int r = 0; r < NR; ++r) {
+                s_off[r] = o;
+                o += s_len[r];
+            }
+            s_off[NR] = o;
+        }
+        __syncthreads();
+        for (int i = br.t0 + tid; i < br.t1; i += BT) {
+            T xa[D];
+            L::pos(g.A[i], xa);
+            const int ki = g.ckey[i];
+            const int cxi = ki - rowbase;
+            const int nslots = g.nl_cnt[i];
+            for (int r = 0; r < NR; ++r) {
+                const int dm = (D == 3) ? (r % 3 - 1) : 0;
+                const int ds = (D == 3) ? (r / 3 - 1) : (r - 1);
+                const int rk = rowbase + (ds * nm + dm) * nx;
+                const int lo = g.cell_start[rk + cxi - 1], hi = g.cell_start[rk + cxi + 2];
+                const int jbase = s_w0a[r] - s_off[r];
+                for (int j = lo; j < hi; ++j) {
+                    if (j == i) continue;
+                    T xb[D], r2 = T(0);
+                    L::pos(g.A[j], xb);
+#pragma unroll
+                    for (int k = 0; k < D; ++k) r2 += (xa[k] - xb[k]) * (xa[k] - xb[k]);
+                    if (!(r2 <= g.phys.H2)) continue;
+                    const unsigned want = (unsigned)(j - jbase);
+                    bool found = false;
+                    for (int k = 0; k < nslots && !found; ++k) {
+                        const uint4 v = g.nl[(size_t)(k >> 3) * g.nl_stride + (size_t)i];
+                        const unsigned w = (k & 4) ? ((k & 2) ? v.w : v.z) : ((k & 2) ? v.y : v.x);
+                        found = ((((k & 1) ? (w >> 16) : w) & LIST_INDEX_MASK) == want);
+                    }
+                    missing += found ? 0 : 1;
+                }
+            }
+        }
+    }
+    if (missing) atomicAdd((unsigned long long *)&g.ctl->list_missing, (unsigned long long)missing);
 }
 
 // Diagnostic (sphb200_get_stat "list_wavefronts"): the shared-memory cost model of sph_listorder.h

@@ -396,7 +396,7 @@ int Sim<T, D>::slab_step_body(cudaEvent_t *ev, bool host_synced, cudaEvent_t *xe
     EV(6);
     if ((rc = slab_pass(1, A.p, B.p, xev ? xev + 4 : nullptr))) return rc;   // S11, S14-S18 + halo state n+1
     EV(7);
-    k_step_end<<<1, 1, 0, stream>>>(d_ctl.p);                         // S19
+    k_step_end<<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p);                         // S19
     ++launches;
     EV(8);
 #undef EV
@@ -475,7 +475,7 @@ int Sim<T, D>::slab_stage_times(double *ms_out, int cnt) {
     if ((rc = slab_allreduce_ctl())) return rc;
     CKS(cudaEventRecord(hev[2], stream));
     k_step_control<T><<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, ph.h, ph.c0, (T)prm.cfl, lists_on() ? opt_skin * prm.H : 0.0,
-                                           motion_vmax(), 1);
+                                           motion_vmax(), 1, opt_list_local);
     ++launches;
     CKS(cudaEventRecord(hev[3], stream));
     if ((rc = sync_ctl())) return rc;

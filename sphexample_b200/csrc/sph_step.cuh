@@ -99,12 +99,19 @@ __global__ void k_reduce_dt_dx(const typename Lay<T, D>::TA *__restrict__ A, con
 // (sph_control.h holds the logic, shared with the CPU tests).
 template <class T>
 __global__ void k_step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, double list_skin, double motion_vmax,
-                               int pause_on_rebuild) {
-    step_control<T>(ctl, grid, h, c0, cfl, list_skin, motion_vmax, pause_on_rebuild);
+                               int pause_on_rebuild, int list_local) {
+    step_control<T>(ctl, grid, h, c0, cfl, list_skin, motion_vmax, pause_on_rebuild, list_local);
 }
 
-// UpdateMetaData!, src/SPHCellList.jl:679-685 (S19)
-__global__ void k_step_end(Ctl *ctl) { step_end(ctl); }
+// UpdateMetaData!, src/SPHCellList.jl:679-685 (S19) (+ the list-maintenance accounting of the step)
+__global__ void k_step_end(Ctl *ctl, const GridInfo *grid) {
+    if (!(ctl->error || ctl->done || !ctl->step_open) && ctl->bricks_flagged > 0) {
+        ctl->list_build_equiv += (double)ctl->bricks_flagged / (double)max(1, grid->nbricks);
+        ctl->n_list_builds += 1;
+    }
+    ctl->bricks_flagged = 0;
+    step_end(ctl);
+}
 
 // any change of positions or cells outside the step sequence voids the neighbour lists
 __global__ void k_invalidate_lists(Ctl *ctl) {

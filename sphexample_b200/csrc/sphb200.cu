@@ -190,6 +190,10 @@ class Sim final : public sphb200_sim {
     int opt_compact, opt_tma, opt_smem_kb, opt_batch;
     int opt_lists, opt_lcap, opt_list_smem_kb;   // per-particle neighbour lists (sph_ring.cuh)
     int opt_list_reorder;                        // bank-aware entry order (sph_listorder.h, k_list_reorder)
+    int opt_list_local;                          // per-brick list validity (brick_list_decision) instead of one global bound
+    int opt_verify_lists = 0;                    // test hook: count listed-pair misses before every pass (k_list_verify)
+    DevBuf<float> vbox, brick_move;              // per-cell velocity boxes (2 buffers x 6 floats), per-brick displacement bounds
+    DevBuf<int> brick_flag;
     double opt_skin;                             // list skin as a fraction of H
     DevBuf<uint4> nl;
     DevBuf<int> nl_cnt;
@@ -241,8 +245,9 @@ class Sim final : public sphb200_sim {
         opt_lists = env_int("SPHB200_LISTS", (sizeof(T) == 4 || D == 2) ? 1 : 0);
         opt_lcap = env_int("SPHB200_LCAP", D == 3 ? 320 : 96);
         opt_list_smem_kb = env_int("SPHB200_LIST_SMEM_KB", 0);    // > 0: pretend a ring slot holds only this much (tests of the overflow fallback)
-        opt_skin = env_int("SPHB200_SKIN_PCT", 10) * 0.01;
+        opt_skin = env_int("SPHB200_SKIN_PCT", 4) * 0.01;       // r2q sweep with per-brick rebuilds: 3 % .. 10 % -> 871 / 874 / 867 / 858 / 848 / 818 Mpu/s
         opt_list_reorder = env_int("SPHB200_LIST_REORDER", 1);
+        opt_list_local = env_int("SPHB200_LIST_LOCAL", 1);
         am.ax_s = D - 1;   // default: the reference's most significant axis
         am.ax_m = (D == 3) ? 1 : 0;
         build_phys();
@@ -340,6 +345,8 @@ class Sim final : public sphb200_sim {
         else if (k == "lcap") opt_lcap = std::max(8, ((int)value + 7) & ~7);
         else if (k == "list_smem_kb") opt_list_smem_kb = (int)value;
         else if (k == "list_reorder") opt_list_reorder = (int)value;
+        else if (k == "list_local") opt_list_local = (int)value;
+        else if (k == "verify_lists") opt_verify_lists = (int)value;
         else return fail(SPHB200_EINVAL, "unknown option '%s'", k.c_str());
         return SPHB200_OK;
     }
@@ -350,7 +357,9 @@ class Sim final : public sphb200_sim {
         CK(cudaSetDevice(device));
         int rc = sync_ctl();
         if (rc) return rc;
-        if (k == "list_builds") *value = h_ctl->n_list_builds;
+        if (k == "list_builds") *value = h_ctl->list_build_equiv;        // in units of "every brick once"
+        else if (k == "list_build_steps") *value = h_ctl->n_list_builds;   // steps in which at least one brick was rebuilt
+        else if (k == "list_missing") *value = (double)h_ctl->list_missing;
         else if (k == "list_off") *value = h_ctl->list_off || h_ctl->list_fail;
         else if (k == "list_fail_reason") *value = h_ctl->list_fail ? h_ctl->list_fail : h_ctl->list_fail_last;
         else if (k == "halo_bytes_per_step") *value = (double)slab.halo_bytes_per_step;
@@ -447,6 +456,9 @@ class Sim final : public sphb200_sim {
         row_cap = cap / 3 + 1;
         brick_cap = (int)std::min<long long>((long long)(n_alloc / 8) + row_cap + 16, INT_MAX);
         CK(bricks.alloc((size_t)brick_cap));
+        CK(brick_move.alloc((size_t)brick_cap));
+        CK(brick_flag.alloc((size_t)brick_cap));
+        CK(vbox.alloc((size_t)(cap + 8) * 12));
         return SPHB200_OK;
     }
 
@@ -808,6 +820,7 @@ class Sim final : public sphb200_sim {
         g.lcap = opt_lcap;
         g.list_cap_cand = list_cap_cand();
         g.list_reorder = opt_list_reorder;
+        g.brick_flag = brick_flag.p;
         const double Hs = prm.H * (1.0 + opt_skin);
         g.Hs2 = (T)(Hs * Hs);
         g.force_cull = cull_force;
@@ -853,6 +866,14 @@ class Sim final : public sphb200_sim {
     // the physics-free list build + the bank-aware reorder (both run only when k_step_control raised ctl->list_build)
     template <bool GEN>
     int launch_list_build() {
+        if (opt_list_local) {   // which bricks need new lists (everything else in this function skips the others)
+            const size_t bs = (size_t)(cell_cap + 8) * 6;
+            k_cell_vbox<T, D><<<grid_for(cell_cap), 256, 0, stream>>>(B.p, cell_start.p, d_grid.p, d_ctl.p, vbox.p, bs);
+            k_brick_bounds<D><<<num_sms * 8, 256, 0, stream>>>(d_ctl.p, d_grid.p, bricks.p, ckey.p, vbox.p, bs, brick_move.p,
+                                                                           brick_flag.p, opt_skin * prm.H);
+            launches += 2;
+            CK(cudaGetLastError());
+        }
         auto kern = k_list_build<T, D, GEN, BT>;
         const int list_bytes = LIST_CAP * BT * 2;   // append buffer
         int smem = std::min(opt_smem_kb, 200) * 1024;
@@ -870,8 +891,8 @@ class Sim final : public sphb200_sim {
             auto rk = k_list_reorder<BT>;
             const int rsmem = (REORDER_MAX_SLOTS + REORDER_OVF_CAP) * BT * 2;
             if ((rc = configure_kernel(rk, BT, rsmem, &ctas))) return rc;
-            rk<<<persistent_blocks(ctas), BT, rsmem, stream>>>(d_ctl.p, d_grid.p, bricks.p, (unsigned)(list_cap_cand() - 8), nl.p, nl_cnt.p,
-                                                             nl_stride, opt_lcap);
+            rk<<<persistent_blocks(ctas), BT, rsmem, stream>>>(d_ctl.p, d_grid.p, bricks.p, brick_flag.p, (unsigned)(list_cap_cand() - 8), nl.p,
+                                                             nl_cnt.p, nl_stride, opt_lcap);
             ++launches;
             CK(cudaGetLastError());
         }
@@ -911,6 +932,13 @@ class Sim final : public sphb200_sim {
             // cull kernel or the list kernel
             int rc = ensure_lists();
             if (rc) return rc;
+            if (opt_verify_lists && brick_part != 2) {
+                InteractArgs<T, D> g;
+                fill_args(g, pass, epilogue);
+                if (generic) k_list_verify<T, D, true, BT><<<num_sms * 2, BT, 0, stream>>>(g, pass);
+                else k_list_verify<T, D, false, BT><<<num_sms * 2, BT, 0, stream>>>(g, pass);
+                ++launches;
+            }
             if ((rc = launch_cull(pass, epilogue, 0))) return rc;
             if (generic) return pass ? launch_ring_t<1, true>(epilogue) : launch_ring_t<0, true>(epilogue);
             return pass ? launch_ring_t<1, false>(epilogue) : launch_ring_t<0, false>(epilogue);
@@ -958,7 +986,7 @@ class Sim final : public sphb200_sim {
         int rc;
         if (slab.active && (rc = slab_allreduce_ctl())) return rc;
         k_step_control<T><<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, ph.h, ph.c0, (T)prm.cfl,
-                                               lists_on() ? opt_skin * prm.H : 0.0, motion_vmax(), slab.active ? 1 : 0);
+                                               lists_on() ? opt_skin * prm.H : 0.0, motion_vmax(), slab.active ? 1 : 0, opt_list_local);
         launches += 2;
         CK(cudaGetLastError());
         return SPHB200_OK;
@@ -983,7 +1011,7 @@ class Sim final : public sphb200_sim {
         EV(6);
         if ((rc = launch_interact(1, EPI_FUSED))) return rc;              // S11, S14-S18  "08", "03", "09", "10", "11"
         EV(7);
-        k_step_end<<<1, 1, 0, stream>>>(d_ctl.p);                         // S19 "12 Update MetaData"
+        k_step_end<<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p);                         // S19 "12 Update MetaData"
         ++launches;
         CK(cudaGetLastError());
         EV(8);

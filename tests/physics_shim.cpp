@@ -179,6 +179,11 @@ extern "C" int shim_rainbow_order(const unsigned short *entries, int n_slots, in
     return ok ? 1 : 0;
 }
 
+// per-brick list validity (brick_list_decision): returns 1 when the brick must be rebuilt; *move is updated
+extern "C" int shim_brick_decision(float *move, float D, double dt_prev, double dt2, double skin) {
+    return brick_list_decision(move, D, dt_prev, dt2, skin) ? 1 : 0;
+}
+
 // step-by-step variant of shim_control_trace for tests whose particle motion depends on the dt decided here
 struct ShimCtl { Ctl ctl; GridInfo grid; };
 extern "C" void *shim_ctl_new(double delta_x0) {

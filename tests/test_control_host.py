@@ -163,3 +163,47 @@ def test_list_bound_holds_for_actual_symplectic_motion(shim):  # noqa: F811
     finally:
         shim.shim_ctl_free(ctl)
     assert builds >= 3 and uses > 2 * builds                                       # the lists were reused, and rebuilt as particles moved
+
+
+def test_brick_bound_holds_for_relative_motion(shim):  # noqa: F811
+    """Per-brick list validity (brick_list_decision, csrc/sph_control.h): a cloud that moves FAST as a
+    whole but deforms slowly.  The decision sees only D = the diagonal of the velocity bounding box at
+    the two step heads; whenever it keeps the lists, every pair within H at the pass's positions must
+    have been within H + skin at the last build.  The global rule (2 dt max|v|) would rebuild ~20x
+    more often here."""
+    rng = np.random.default_rng(7)
+    n, Hc = 250, 2 * H
+    skin = 0.1 * Hc
+    x = rng.uniform(0, 5 * Hc, (n, 3))
+    v = np.array([25.0, -10.0, 5.0]) + rng.normal(0, 0.3, (n, 3))       # bulk speed ~27 m/s, relative ~1 m/s
+    shim.shim_brick_decision.argtypes = [C.POINTER(C.c_float), C.c_float, C.c_double, C.c_double, C.c_double]
+    move = C.c_float(0.0)
+
+    def within(p, r):
+        d2 = ((p[:, None, :] - p[None, :, :]) ** 2).sum(-1)
+        return d2 <= r * r
+
+    def box_diag(*vs):
+        allv = np.concatenate(vs)
+        return float(np.linalg.norm(allv.max(0) - allv.min(0)))
+
+    listed, v_prev, dt_prev, builds, global_builds, gmove = within(x, Hc + skin), v.copy(), 0.0, 1, 1, 0.0
+    for step in range(400):
+        dt = CFL * H / (C0 + 5.0)
+        a = rng.normal(0, 1.5e2, (n, 3)) * (1.0 + np.sin(0.07 * step)) + np.array([0.0, 0.0, -9.81])
+        D = box_diag(v, v_prev) * 1.0001
+        if shim.shim_brick_decision(C.byref(move), D, dt_prev, dt / 2, skin):
+            listed = within(x, Hc + skin)
+            builds += 1
+        # what the global rule would have done
+        vmax = max(np.linalg.norm(v, axis=1).max(), np.linalg.norm(v_prev, axis=1).max())
+        gmove += dt_prev * vmax
+        if gmove + dt / 2 * vmax > 0.49 * skin:
+            gmove, global_builds = 0.0, global_builds + 1
+        assert not np.any(within(x, Hc) & ~listed), f"pass 1 of step {step}"
+        x_half = x + v * (dt / 2)
+        assert not np.any(within(x_half, Hc) & ~listed), f"pass 2 of step {step}"
+        v_new = v + a * dt
+        x = x + (v + v_new) / 2 * dt
+        v_prev, v, dt_prev = v, v_new, dt
+    assert builds >= 3 and global_builds > 4 * builds, (builds, global_builds)

@@ -101,3 +101,45 @@ def test_stage_level_calls_void_the_lists(oracle_lib):
     util.check(util.relerr(st["Density"], util.by_id(o.ids, o.get("rho"))), 1e-11)
     sim.close()
 
+
+
+@pytest.mark.parametrize("name,steps,vel", [("c1_2d_f64", 150, 3.0), ("3d_f32", 120, 3.0), ("3d_f32", 60, 0.5)])
+@pytest.mark.parametrize("local", [1, 0])
+def test_no_listed_pair_is_ever_missing(name, steps, vel, local):
+    """on-device proof of the list bookkeeping (option verify_lists, k_list_verify): before EVERY pass that
+    runs on the lists, every pair of a particle's stale-cell window that lies within H must be in its
+    list — with the per-brick displacement bounds (list_local, the default) and with the global one"""
+    mk = {"c1_2d_f64": lambda: util.case_c1("float64"), "3d_f32": lambda: util.case_3d_small("float32")}[name]
+    case = util.perturb(mk(), vel_scale=vel)
+    sim = Simulation(util.params_of(case))
+    sim.set_option("lists", 1)
+    sim.set_option("list_local", local)
+    sim.set_option("verify_lists", 1)
+    sim.upload(case.particles)
+    rep = sim.step(steps, reset_delta_x=True)
+    assert rep["iteration"] == steps
+    assert sim.stat("list_off") == 0 and sim.stat("list_builds") >= 1
+    assert sim.stat("list_missing") == 0
+    builds, build_steps = sim.stat("list_builds"), sim.stat("list_build_steps")
+    sim.close()
+    if local and vel >= 3.0:
+        assert build_steps >= 2          # lists were refreshed on the way ...
+    assert builds < steps                # ... but never as often as every step
+
+
+def test_local_list_bounds_rebuild_less_than_the_global_one():
+    """a dam break at rest that starts to collapse: the walls and most of the column barely move
+    relative to their neighbours, so the per-brick bounds rebuild a fraction of what the global bound does"""
+    out = {}
+    for local in (0, 1):
+        case = util.perturb(util.case_3d_small("float32"), vel_scale=2.0)
+        sim = Simulation(util.params_of(case))
+        sim.set_option("lists", 1)
+        sim.set_option("list_local", local)
+        sim.upload(case.particles)
+        sim.step(100, reset_delta_x=True)
+        out[local] = (sim.stat("list_builds"), sim.download(order="id", fields=("Position", "Velocity", "Density")))
+        sim.close()
+    assert out[1][0] < out[0][0]
+    for f in ("Position", "Velocity", "Density"):
+        util.check(util.relerr(out[1][1][f], out[0][1][f]), 4e-5)

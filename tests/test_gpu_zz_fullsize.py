@@ -93,7 +93,7 @@ def test_fused_steps_match_oracle_at_full_size(oracle_lib, c3):
     orep = o.report()
     assert rep["iteration"] == orep["iteration"] == nsteps
     assert rep["total_time"] == pytest.approx(orep["total_time"], rel=1e-5)
-    assert sim.stat("list_builds") >= 2 and sim.stat("list_off") == 0
+    assert sim.stat("list_build_steps") >= 2 and sim.stat("list_off") == 0
     st = sim.download(order="id")
     ids = o.ids
     assert np.all(np.isfinite(st["Velocity"])) and np.all(np.isfinite(st["Density"]))
