@@ -475,7 +475,7 @@ int Sim<T, D>::slab_stage_times(double *ms_out, int cnt) {
     if ((rc = slab_allreduce_ctl())) return rc;
     CKS(cudaEventRecord(hev[2], stream));
     k_step_control<T><<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, ph.h, ph.c0, (T)prm.cfl, lists_on() ? opt_skin * prm.H : 0.0,
-                                           motion_vmax(), 1, opt_list_local);
+                                           motion_vmax(), 1, opt_list_local, 0ull, 0ull);
     ++launches;
     CKS(cudaEventRecord(hev[3], stream));
     if ((rc = sync_ctl())) return rc;

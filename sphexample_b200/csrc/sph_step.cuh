@@ -97,10 +97,17 @@ __global__ void k_reduce_dt_dx(const typename Lay<T, D>::TA *__restrict__ A, con
 
 // One thread: S0/S1 completion, the S2 decision, the while-condition and the neighbour-list state
 // (sph_control.h holds the logic, shared with the CPU tests).
+// h_rebuild / h_lists: handles of the CUDA-graph conditional nodes that hold the UpdateNeighbors!
+// chain and the list maintenance of a captured step (0 outside a conditional step graph): the
+// kernels behind them run only in the steps that need them instead of starting up empty.
 template <class T>
 __global__ void k_step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, double list_skin, double motion_vmax,
-                               int pause_on_rebuild, int list_local) {
+                               int pause_on_rebuild, int list_local, cudaGraphConditionalHandle h_rebuild,
+                               cudaGraphConditionalHandle h_lists) {
     step_control<T>(ctl, grid, h, c0, cfl, list_skin, motion_vmax, pause_on_rebuild, list_local);
+    const bool live = !ctl->error && !ctl->done;
+    if (h_rebuild) cudaGraphSetConditional(h_rebuild, (live && ctl->do_rebuild) ? 1u : 0u);
+    if (h_lists) cudaGraphSetConditional(h_lists, (live && ctl->list_build != 0) ? 1u : 0u);
 }
 
 // UpdateMetaData!, src/SPHCellList.jl:679-685 (S19) (+ the list-maintenance accounting of the step)

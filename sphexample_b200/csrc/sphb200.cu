@@ -239,6 +239,9 @@ class Sim final : public sphb200_sim {
         opt_smem_kb = env_int("SPHB200_SMEM_KB", sizeof(T) == 8 ? 40 : 24);
         opt_batch = env_int("SPHB200_BATCH", 64);
         opt_graph = env_int("SPHB200_GRAPH", 1);
+        // measured on B200 (profiles/r2r_configs.jsonl): the conditional nodes cost as much as the ~17 empty
+        // kernels they replace (C1 57 vs 60, C2 304 vs 317, C5 19.6 vs 20.4 Mpu/s) — off by default
+        opt_graph_cond = env_int("SPHB200_GRAPH_COND", 0);
         // lists: fp32 only by default (an fp64 3D window does not fit shared memory), never with
         // PlanarShifting (the shifting displacement is not covered by the |v| dt bound)
         // (2D fp64 windows fit too: C2 186 -> 325 Mpu/s, profiles/r1m_configs.jsonl)
@@ -335,6 +338,7 @@ class Sim final : public sphb200_sim {
         std::string k(name ? name : "");
         drop_step_graph();
         if (k == "graph") { opt_graph = (int)value; return SPHB200_OK; }
+        if (k == "graph_cond") { opt_graph_cond = (int)value; return SPHB200_OK; }
         if (k == "compact") opt_compact = (int)value;
         else if (k == "tma") opt_tma = (int)value;
         else if (k == "smem_kb") opt_smem_kb = (int)value;
@@ -986,38 +990,51 @@ class Sim final : public sphb200_sim {
         int rc;
         if (slab.active && (rc = slab_allreduce_ctl())) return rc;
         k_step_control<T><<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, ph.h, ph.c0, (T)prm.cfl,
-                                               lists_on() ? opt_skin * prm.H : 0.0, motion_vmax(), slab.active ? 1 : 0, opt_list_local);
+                                               lists_on() ? opt_skin * prm.H : 0.0, motion_vmax(), slab.active ? 1 : 0, opt_list_local,
+                                               capturing_cond ? cond_rebuild : 0ull, capturing_cond ? cond_lists : 0ull);
         launches += 2;
         CK(cudaGetLastError());
         return SPHB200_OK;
     }
-    // phase B: S2 .. S19.  ev (optional, 10 events): stage boundaries for stage_times()
+    // phase B: S2 .. S19, in the pieces a conditional step graph is assembled from.
+    // ev (optional, 10 events): stage boundaries for stage_times()
+    int enqueue_body_rebuild() { return enqueue_rebuild(); }                  // S2  "02 Calculate IndexCounter"
+    int enqueue_body_pre(cudaEvent_t *ev = nullptr) {
+        int rc;
+        if ((rc = enqueue_motion(-1.0))) return rc;                           // S3  "Motion"
+        if ((rc = enqueue_snapshots())) return rc;
+        if (ev) CK(cudaEventRecord(ev[2], stream));
+        if (prm.mdbc && (rc = enqueue_mdbc())) return rc;                     // S6  "04 Apply MDBC before Half TimeStep"
+        return SPHB200_OK;
+    }
+    int enqueue_body_passes(cudaEvent_t *ev = nullptr) {
+        int rc;
+        if ((rc = launch_interact(0, EPI_FUSED))) return rc;                  // S4-S10, S13  "05", "03", "06", "07"
+        if (ev) CK(cudaEventRecord(ev[5], stream));
+        if ((rc = enqueue_motion(-1.0))) return rc;                           // S12 "Motion"
+        if (ev) CK(cudaEventRecord(ev[6], stream));
+        if ((rc = launch_interact(1, EPI_FUSED))) return rc;                  // S11, S14-S18  "08", "03", "09", "10", "11"
+        if (ev) CK(cudaEventRecord(ev[7], stream));
+        k_step_end<<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p);                   // S19 "12 Update MetaData"
+        ++launches;
+        CK(cudaGetLastError());
+        have_half = true;
+        have_cells = true;
+        return SPHB200_OK;
+    }
     int enqueue_step_body(cudaEvent_t *ev = nullptr) {
         int rc;
 #define EV(k) if (ev) CK(cudaEventRecord(ev[k], stream))
         EV(0);
-        if ((rc = enqueue_rebuild())) return rc;                          // S2  "02 Calculate IndexCounter"
+        if ((rc = enqueue_body_rebuild())) return rc;
         EV(1);
-        if ((rc = enqueue_motion(-1.0))) return rc;                       // S3  "Motion"
-        if ((rc = enqueue_snapshots())) return rc;
-        EV(2);
-        if (prm.mdbc && (rc = enqueue_mdbc())) return rc;                 // S6  "04 Apply MDBC before Half TimeStep"
+        if ((rc = enqueue_body_pre(ev))) return rc;
         EV(3);
-        if ((rc = enqueue_list_build())) return rc;                       //     neighbour-list maintenance (no reference stage)
+        if ((rc = enqueue_list_build())) return rc;                           //     neighbour-list maintenance (no reference stage)
         EV(4);
-        if ((rc = launch_interact(0, EPI_FUSED))) return rc;              // S4-S10, S13  "05", "03", "06", "07"
-        EV(5);
-        if ((rc = enqueue_motion(-1.0))) return rc;                       // S12 "Motion"
-        EV(6);
-        if ((rc = launch_interact(1, EPI_FUSED))) return rc;              // S11, S14-S18  "08", "03", "09", "10", "11"
-        EV(7);
-        k_step_end<<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p);                         // S19 "12 Update MetaData"
-        ++launches;
-        CK(cudaGetLastError());
+        if ((rc = enqueue_body_passes(ev))) return rc;
         EV(8);
 #undef EV
-        have_half = true;
-        have_cells = true;
         return SPHB200_OK;
     }
 
@@ -1042,11 +1059,86 @@ class Sim final : public sphb200_sim {
     cudaGraphExec_t step_exec = nullptr;
     int64_t step_graph_launches = 0;
     int opt_graph = 1;
+    int opt_graph_cond = 0;   // UpdateNeighbors! and the list maintenance behind CUDA-graph conditional (IF) nodes
+    cudaGraphConditionalHandle cond_rebuild = 0, cond_lists = 0;   // non-zero only while a conditional step graph is captured / alive
+    bool capturing_cond = false;   // the handles are kernel arguments ONLY inside that graph (plain launches must not touch them)
     void drop_step_graph() {
         if (step_exec) cudaGraphExecDestroy(step_exec);
         if (step_graph) cudaGraphDestroy(step_graph);
         step_exec = nullptr;
         step_graph = nullptr;
+        cond_rebuild = cond_lists = 0;
+    }
+    // The step as ONE graph whose rarely needed parts sit behind conditional nodes:
+    //   head (reductions, control: sets the two conditions) -> IF(rebuild){UpdateNeighbors! chain}
+    //   -> motion, snapshots, mDBC -> IF(lists){velocity boxes, brick bounds, list build, reorder} -> passes, step end.
+    // A step that neither rebuilds cells nor lists is ~10 kernel nodes instead of ~30, which is what a
+    // 10^3-10^5 particle case (shorter than its own launch overhead) is made of.  Returns false (and
+    // leaves no graph behind) if the driver refuses any part: the caller then captures the flat graph.
+    bool capture_conditional_step_graph() {
+        const cudaStreamCaptureMode mode = cudaStreamCaptureModeThreadLocal;
+        cudaGraph_t g = nullptr;
+        bool ok = cudaGraphCreate(&g, 0) == cudaSuccess;
+        ok = ok && cudaGraphConditionalHandleCreate(&cond_rebuild, g, 0, cudaGraphCondAssignDefault) == cudaSuccess;
+        ok = ok && cudaGraphConditionalHandleCreate(&cond_lists, g, 0, cudaGraphCondAssignDefault) == cudaSuccess;
+        std::vector<cudaGraphNode_t> tail;
+        // one captured segment appended to graph `dst` behind `tail`; the new tail is returned in `tail`
+        auto segment = [&](cudaGraph_t dst, bool track_tail, auto &&body) -> bool {
+            if (cudaStreamBeginCaptureToGraph(stream, dst, tail.empty() || dst != g ? nullptr : tail.data(), nullptr,
+                                              dst != g ? 0 : tail.size(), mode) != cudaSuccess)
+                return false;
+            const int rc = body();
+            bool good = rc == 0;
+            if (good && track_tail) {
+                cudaStreamCaptureStatus st;
+                const cudaGraphNode_t *deps = nullptr;
+                size_t ndeps = 0;
+                good = cudaStreamGetCaptureInfo(stream, &st, nullptr, nullptr, &deps, &ndeps) == cudaSuccess;
+                if (good) tail.assign(deps, deps + ndeps);
+            }
+            cudaGraph_t out = nullptr;
+            good = (cudaStreamEndCapture(stream, &out) == cudaSuccess) && good;
+            return good;
+        };
+        auto conditional = [&](cudaGraphConditionalHandle h, auto &&body) -> bool {
+            cudaGraphNodeParams p = {};
+            p.type = cudaGraphNodeTypeConditional;
+            p.conditional.handle = h;
+            p.conditional.type = cudaGraphCondTypeIf;
+            p.conditional.size = 1;
+            cudaGraphNode_t node = nullptr;
+            if (cudaGraphAddNode(&node, g, tail.data(), tail.size(), &p) != cudaSuccess) return false;
+            cudaGraph_t inner = p.conditional.phGraph_out[0];
+            std::vector<cudaGraphNode_t> saved;
+            saved.swap(tail);
+            const bool good = segment(inner, false, body);
+            tail.assign(1, node);
+            return good;
+        };
+        capturing_cond = true;
+        ok = ok && segment(g, true, [&] { return enqueue_step_head(); });
+        capturing_cond = false;
+        ok = ok && conditional(cond_rebuild, [&] { return enqueue_body_rebuild(); });
+        ok = ok && segment(g, true, [&] { return enqueue_body_pre(); });
+        if (lists_on()) ok = ok && conditional(cond_lists, [&] { return enqueue_list_build(); });
+        ok = ok && segment(g, true, [&] { return enqueue_body_passes(); });
+        ok = ok && cudaGraphInstantiate(&step_exec, g, 0) == cudaSuccess;
+        if (!ok) {
+            cudaGetLastError();
+            cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+                cudaGraph_t junk = nullptr;
+                cudaStreamEndCapture(stream, &junk);
+            }
+            cudaGetLastError();
+            if (step_exec) cudaGraphExecDestroy(step_exec);
+            step_exec = nullptr;
+            if (g) cudaGraphDestroy(g);
+            cond_rebuild = cond_lists = 0;
+            return false;
+        }
+        step_graph = g;
+        return true;
     }
     int enqueue_step() {
         int rc;
@@ -1055,6 +1147,15 @@ class Sim final : public sphb200_sim {
         if (!opt_graph || !have_half || !have_cells || stream == nullptr) {   // first steps: arguments still change, attributes get set
             if ((rc = enqueue_step_head())) return rc;
             return enqueue_step_body();
+        }
+        if (!step_exec && opt_graph_cond) {
+            const int64_t l0 = launches;
+            if (capture_conditional_step_graph()) {
+                step_graph_launches = launches - l0;
+            } else {
+                opt_graph_cond = 0;   // flat capture below
+            }
+            launches = l0;
         }
         if (!step_exec) {
             const int64_t l0 = launches;

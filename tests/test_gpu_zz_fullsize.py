@@ -192,3 +192,28 @@ def test_gpu_matches_the_committed_oracle_outputs(name, mk):
     prm = util.params_of(case)
     p_ref = (prm.c0 * prm.c0 * prm.rho0 / 7.0) * ((g["rho"] / prm.rho0) ** 7 - 1.0)
     util.check(util.relerr(st["Pressure"][pick], p_ref), 1e-7)
+
+
+@pytest.mark.parametrize("name", ["c1_2d_f64", "3d_f32"])
+def test_conditional_step_graph_is_bitwise_identical(name):
+    """option graph_cond (UpdateNeighbors! and the list maintenance behind CUDA-graph IF nodes; off by
+    default: measured no faster than the empty kernels it skips) must not change a single bit"""
+    mk = {"c1_2d_f64": lambda: util.case_c1("float64"), "3d_f32": lambda: util.case_3d_small("float32")}[name]
+    out = []
+    for cond in (0, 1):
+        case = util.perturb(mk(), vel_scale=2.0)
+        sim = Simulation(util.params_of(case))
+        sim.set_option("graph_cond", cond)
+        import torch
+        stream = torch.cuda.Stream()
+        sim.set_stream(stream.cuda_stream)
+        sim.upload(case.particles)
+        rep = sim.step(90, reset_delta_x=True)
+        torch.cuda.synchronize()
+        out.append((rep, sim.download(order="id")))
+        sim.close()
+    (r0, s0), (r1, s1) = out
+    assert r0["iteration"] == r1["iteration"] == 90 and r0["n_rebuilds"] == r1["n_rebuilds"] >= 2
+    assert r0["total_time"] == r1["total_time"]
+    for f in ("Position", "Velocity", "Density", "Pressure"):
+        assert np.array_equal(s0[f], s1[f]), f
