@@ -385,9 +385,9 @@ def run_ours(args, rank, world, local_rank):
     value = n * args.steps / (ms * 1e-3) / 1e6
 
     # ---- per-stage device times (CUDA events on the library's stream, extra steps, L2 flushed) ----
-    # mean over `reps` steps that did NOT rebuild cells or lists in the pass stages; the list / cell
-    # rebuild stages are reported as their mean over all sampled steps (amortised cost per step)
-    reps = 12
+    # every stage: mean over `reps` sampled steps (so the rare cell rebuild and its full list build appear at
+    # their amortised cost per step); the two pass stages used for the roofline: median of the samples
+    reps = 48
     samples = []
     for _ in range(reps):
         flush.zero_()

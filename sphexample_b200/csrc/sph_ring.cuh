@@ -1030,12 +1030,13 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
                     }
                 }
             };
+            const int pf_last = min(last_chunk, mchunk - 1);   // nothing beyond the warp's longest list is fetched from DRAM
             for (int c0 = 0; c0 < mchunk; c0 += LIST_PF) {
 #pragma unroll
                 for (int d = 0; d < LIST_PF; ++d) {
                     if (d == 0 || c0 + d < mchunk) {   // (warp-uniform)
                         chunk_body(c0 + d, pf[d]);
-                        if (c0 + d + LIST_PF <= last_chunk) pp[d] += (size_t)LIST_PF * lstride;
+                        if (c0 + d + LIST_PF <= pf_last) pp[d] += (size_t)LIST_PF * lstride;   // (else: re-read, an L2 hit)
                         pf[d] = ld_nc_v4(pp[d]);
                     }
                 }

@@ -136,6 +136,53 @@ __global__ void k_pack_upload(int n, const T *__restrict__ pos, const T *__restr
     }
 }
 
+// upload helpers: defaults for the optional columns and the bounding box, without host passes over the table
+__global__ void k_fill_defaults(int n, unsigned long long *group, long long *id) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (group) group[i] = 1ull;
+        if (id) id[i] = (long long)i + 1;
+    }
+}
+// min / max of every coordinate -> out[0..2] = min, out[3..5] = max, out[6] != 0: a non-finite coordinate
+template <class T, int D>
+__global__ void k_upload_bbox(int n, const T *__restrict__ pos, double *out) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    bool bad = false;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const double x = (double)pos[(size_t)i * D + k];
+            bad |= !(x == x) || fabs(x) > 1e300;
+            lo[k] = fmin(lo[k], x);
+            hi[k] = fmax(hi[k], x);
+        }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = warp_min(lo[k]);
+        hi[k] = warp_max(hi[k]);
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+        for (int k = 0; k < D; ++k) {
+            // atomic min / max on doubles by compare-and-swap
+            unsigned long long *plo = (unsigned long long *)&out[k], *phi = (unsigned long long *)&out[3 + k];
+            unsigned long long old = *plo, assumed;
+            do {
+                assumed = old;
+                if (!(lo[k] < __longlong_as_double((long long)assumed))) break;
+                old = atomicCAS(plo, assumed, (unsigned long long)__double_as_longlong(lo[k]));
+            } while (old != assumed);
+            old = *phi;
+            do {
+                assumed = old;
+                if (!(hi[k] > __longlong_as_double((long long)assumed))) break;
+                old = atomicCAS(phi, assumed, (unsigned long long)__double_as_longlong(hi[k]));
+            } while (old != assumed);
+        }
+        if (bad) out[6] = 1.0;
+    }
+}
+
 template <class T, int D>
 __global__ void k_unpack_download(int n, const typename Lay<T, D>::TA *__restrict__ A, const typename Lay<T, D>::TB *__restrict__ B,
                                   const typename Lay<T, D>::TV *__restrict__ accv, T *pos, T *vel, T *acc, T *rho, T *press) {
@@ -410,7 +457,7 @@ class Sim final : public sphb200_sim {
         if (prm.mdbc) { CK(ghost.alloc(na)); CK(ghost2.alloc(na)); CK(rho_new.alloc(na)); CK(has_new.alloc(na)); }
         if (prm.shifting) { CK(gradC.alloc(na)); CK(divr.alloc(na)); }
         if (prm.kernel_output) { CK(ksum.alloc(na)); CK(kgrad.alloc(na)); }
-        CK(stage.alloc(na * (size_t)(sizeof(T) * (4 * D + 2) + 8)));
+        CK(stage.alloc(na * (size_t)(sizeof(T) * (4 * D + 2) + 8) + 256));
         // zero everything the TMA staging may touch beyond n (finite padding)
         CK(cudaMemsetAsync(A.p, 0, na * sizeof(TA), stream)); CK(cudaMemsetAsync(Ah.p, 0, na * sizeof(TA), stream));
         CK(cudaMemsetAsync(B.p, 0, na * sizeof(TB), stream)); CK(cudaMemsetAsync(Bh.p, 0, na * sizeof(TB), stream));
@@ -437,7 +484,7 @@ class Sim final : public sphb200_sim {
         CK(key_tmp.grow(na, 0, stream)); CK(slot_tmp.grow(na, 0, stream)); CK(tmp_idx.grow(na, 0, stream)); CK(perm.grow(na, 0, stream));
         if (prm.shifting) { CK(gradC.grow(na, keep, stream)); CK(divr.grow(na, keep, stream)); }
         if (prm.kernel_output) { CK(ksum.grow(na, keep, stream)); CK(kgrad.grow(na, keep, stream)); }
-        CK(stage.grow(na * (size_t)(sizeof(T) * (4 * D + 2) + 8), 0, stream));
+        CK(stage.grow(na * (size_t)(sizeof(T) * (4 * D + 2) + 8) + 256, 0, stream));
         n_alloc = na;
         {
             int rc = ensure_lists();
@@ -492,20 +539,11 @@ class Sim final : public sphb200_sim {
         if (gp && prm.mdbc) CK(cudaMemcpyAsync(d_gp, gp, vb, cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(d_rho, rho, sb, cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(type.p, ty, (size_t)count, cudaMemcpyHostToDevice, stream));
-        if (grp) {
-            CK(cudaMemcpyAsync(group.p, grp, (size_t)count * 8, cudaMemcpyHostToDevice, stream));
-        } else {
-            std::vector<unsigned long long> ones((size_t)count, 1ull);
-            CK(cudaMemcpyAsync(group.p, ones.data(), (size_t)count * 8, cudaMemcpyHostToDevice, stream));
-            CK(cudaStreamSynchronize(stream));
-        }
-        if (ids) {
-            CK(cudaMemcpyAsync(id.p, ids, (size_t)count * 8, cudaMemcpyHostToDevice, stream));
-        } else {
-            std::vector<long long> seq((size_t)count);
-            std::iota(seq.begin(), seq.end(), 1ll);
-            CK(cudaMemcpyAsync(id.p, seq.data(), (size_t)count * 8, cudaMemcpyHostToDevice, stream));
-            CK(cudaStreamSynchronize(stream));
+        if (grp) CK(cudaMemcpyAsync(group.p, grp, (size_t)count * 8, cudaMemcpyHostToDevice, stream));
+        if (ids) CK(cudaMemcpyAsync(id.p, ids, (size_t)count * 8, cudaMemcpyHostToDevice, stream));
+        if (!grp || !ids) {   // defaults: GroupMarker 1, ID = 1 .. N
+            k_fill_defaults<<<grid_for(count), 256, 0, stream>>>((int)count, grp ? nullptr : group.p, ids ? nullptr : id.p);
+            ++launches;
         }
         k_pack_upload<T, D><<<grid_for(count), 256, 0, stream>>>((int)count, d_pos, vel ? d_vel : nullptr,
                                                                 accel ? d_acc : nullptr, d_rho,
@@ -514,20 +552,19 @@ class Sim final : public sphb200_sim {
                                                                 slab.active ? id.p : nullptr, okey.p);
         ++launches;
         CK(cudaGetLastError());
-        // size the dense cell grid from the host-side bounding box (grown on demand later)
+        // size the dense cell grid from the bounding box of the uploaded positions (grown on demand later)
         {
-            const T *hp = (const T *)pos;
-            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-            for (int64_t i = 0; i < count; ++i)
-                for (int k = 0; k < D; ++k) {
-                    double x = (double)hp[i * D + k];
-                    lo[k] = std::min(lo[k], x);
-                    hi[k] = std::max(hi[k], x);
-                }
+            double *d_bb = (double *)(stage.p + (((4 * vb + sb + 63) / 64) + 1) * 64);   // behind the staged columns (the stage buffer has spare room)
+            double h_bb[7] = {1e300, 1e300, 1e300, -1e300, -1e300, -1e300, 0.0};
+            CK(cudaMemcpyAsync(d_bb, h_bb, sizeof h_bb, cudaMemcpyHostToDevice, stream));
+            k_upload_bbox<T, D><<<grid_for(count), 256, 0, stream>>>((int)count, d_pos, d_bb);
+            ++launches;
+            CK(cudaMemcpyAsync(h_bb, d_bb, sizeof h_bb, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
             long long cells = 1;
             for (int k = 0; k < D; ++k) {
-                double e = (hi[k] - lo[k]) * prm.H_inv + 12.0;
-                if (!(e < 1e9)) return fail(SPHB200_EINVAL, "upload: non-finite or absurd position range");
+                double e = (h_bb[3 + k] - h_bb[k]) * prm.H_inv + 12.0;
+                if (h_bb[6] != 0.0 || !(e < 1e9)) return fail(SPHB200_EINVAL, "upload: non-finite or absurd position range");
                 cells *= (long long)e;
                 if (cells > (1ll << 40)) break;
             }
@@ -565,12 +602,12 @@ class Sim final : public sphb200_sim {
                                                                   d_rho, d_pr);
         ++launches;
         CK(cudaGetLastError());
-        std::vector<long long> hid((size_t)cnt);
-        CK(cudaMemcpyAsync(hid.data(), id.p + off, (size_t)cnt * 8, cudaMemcpyDeviceToHost, stream));
-        std::vector<T> hv;
+        std::vector<long long> hid;
         std::vector<int64_t> order_idx;
-        CK(cudaStreamSynchronize(stream));
         if (order == 1) {
+            hid.resize((size_t)cnt);
+            CK(cudaMemcpyAsync(hid.data(), id.p + off, (size_t)cnt * 8, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
             order_idx.resize((size_t)cnt);
             std::iota(order_idx.begin(), order_idx.end(), 0);
             std::stable_sort(order_idx.begin(), order_idx.end(), [&](int64_t a, int64_t b) { return hid[a] < hid[b]; });
