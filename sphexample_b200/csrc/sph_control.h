@@ -49,7 +49,8 @@ struct Ctl {
     double list_prev_vmax;     // max |v| at the previous step head
     // per-brick ("local") list maintenance, see brick_list_decision below
     int vbox_cur;              // which of the two per-cell velocity-box buffers holds the head-of-step velocities
-    int bricks_flagged;        // bricks whose lists are rebuilt in this step
+    int bricks_flagged;        // bricks whose lists are rebuilt in this step (counted by k_list_build)
+    int bricks_urgent;         // bricks whose displacement bound is used up NOW: only then does the step build at all
     double list_build_equiv;   // builds so far in units of "all bricks once" (what sphb200_get_stat("list_builds") reports)
     double vmax_now;           // max |v| at this step head (incl. moving bodies)
     long long list_missing;    // test hook (option verify_lists): pairs within H found missing from a list in use
@@ -209,15 +210,18 @@ SPH_HD void step_end(Ctl *ctl) {
 // boxes are kept per cell, k_cell_vbox) — a bound on RELATIVE velocities, so a water column that
 // moves as a whole keeps its lists; the global rule of step_control (2 dt max|v|) cannot see that.
 // `move`: accumulated bound through the previous step; the half step of pass 2 adds dt2 D.
-// Returns true when the brick's lists must be rebuilt now (and resets the bound).
-SPH_HD bool brick_list_decision(float *move, float D, double dt_prev, double dt2, double skin) {
+// Returns 2 when the brick's lists must be rebuilt NOW, 1 when they will be within about `lookahead`
+// more steps at the present rate (such bricks are rebuilt along with the urgent ones: a build is a
+// latency-bound launch, so the bricks that are nearly due ride along instead of forcing a build of
+// their own in one of the next steps), 0 otherwise.  *move is advanced, never reset here: the build
+// kernel zeroes the bound of the bricks it actually rebuilds.
+SPH_HD int brick_list_decision(float *move, float D, double dt_prev, double dt2, double skin, double lookahead = 0.0) {
     const float m = *move + (float)dt_prev * D * 1.0001f;   // (rounding of the accumulation never shortens the bound)
-    if ((double)m + dt2 * (double)D > 0.98 * skin) {
-        *move = 0.f;
-        return true;
-    }
     *move = m;
-    return false;
+    const double need = (double)m + dt2 * (double)D;
+    if (need > 0.98 * skin) return 2;
+    if (need + lookahead * 2.0 * dt2 * (double)D > 0.98 * skin) return 1;
+    return 0;
 }
 
 }  // namespace sph

@@ -91,7 +91,8 @@ struct InteractArgs {
     int lcap;                          // list capacity per particle (multiple of 8)
     int list_cap_cand;                 // candidates one ring slot of the list kernel holds; its last 8 records are the sentinels
     int list_reorder;                  // 1: k_list_reorder runs after a build (bank-aware entry order, sph_listorder.h)
-    const int *brick_flag;             // per brick: rebuild its lists in this step (LIST_BUILD_FLAGGED, k_brick_bounds)
+    const int *brick_flag;             // per brick: 2 rebuild now, 1 due soon (rebuilt if the step builds at all), 0 good (k_brick_bounds)
+    float *brick_move;                 // per brick: accumulated relative-displacement bound (reset by the build)
     T Hs2;                             // (H + skin)^2: acceptance radius of a list build
     int force_cull;                    // 1: ignore ctl->list_mode (stage-level entry points)
 };

@@ -107,7 +107,7 @@ __global__ void k_cell_vbox(const typename Lay<T, D>::TB *__restrict__ B, const 
 template <int D>
 __global__ void k_brick_bounds(Ctl *ctl, const GridInfo *grid, const Brick *__restrict__ bricks, const int *__restrict__ ckey,
                                const float *__restrict__ vbox, size_t buf_stride, float *__restrict__ brick_move,
-                               int *__restrict__ brick_flag, double skin) {
+                               int *__restrict__ brick_flag, double skin, double lookahead) {
     if (ctl->error || ctl->done || ctl->list_build == LIST_BUILD_NONE) return;
     constexpr int NR = (D == 3) ? 9 : 3;
     const int nbricks = grid->nbricks, nx = grid->nx, nm = grid->nm;
@@ -118,7 +118,7 @@ __global__ void k_brick_bounds(Ctl *ctl, const GridInfo *grid, const Brick *__re
     int flagged = 0;
     for (int b = warp; b < nbricks; b += nwarps) {
         float move = 0.f;
-        bool flag = true;
+        int flag = 2;
         if (!all) {
             const Brick br = bricks[b];
             const int key0 = ckey[br.t0], key1 = ckey[br.t1 - 1];
@@ -154,15 +154,15 @@ __global__ void k_brick_bounds(Ctl *ctl, const GridInfo *grid, const Brick *__re
             }
             const float Dd = fminf(sqrtf(d2) * 1.0001f, vcap);
             move = brick_move[b];
-            flag = brick_list_decision(&move, Dd, ctl->current_dt, ctl->dt2, skin);
+            flag = brick_list_decision(&move, Dd, ctl->current_dt, ctl->dt2, skin, lookahead);
         }
         if (lane == 0) {
             brick_move[b] = move;
-            brick_flag[b] = flag ? 1 : 0;
-            flagged += flag ? 1 : 0;
+            brick_flag[b] = flag;            // 2 urgent, 1 due soon, 0 good
+            flagged += flag == 2 ? 1 : 0;
         }
     }
-    if (lane == 0 && flagged) atomicAdd(&ctl->bricks_flagged, flagged);
+    if (lane == 0 && flagged) atomicAdd(&ctl->bricks_urgent, flagged);
 }
 
 // =================================================================================================
@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(BT) k_list_build(const InteractArgs<T, D> g) {
     const int npad = (g.grid->n_total + 3) & ~3;
     const T Hs2 = g.Hs2;
     const bool flagged_only = g.ctl->list_build == LIST_BUILD_FLAGGED;
+    if (flagged_only && g.ctl->bricks_urgent == 0) return;   // every brick's lists are still good: no build in this step
 
     for (;;) {
         if (tid == 0) s_brick = atomicAdd(&g.ctl->work_counter[6], 1);
@@ -213,6 +214,10 @@ __global__ void __launch_bounds__(BT) k_list_build(const InteractArgs<T, D> g) {
         if (flagged_only && !g.brick_flag[bidx]) {   // this brick's lists are still good (k_brick_bounds)
             __syncthreads();                         // (s_brick is rewritten at the top of the loop)
             continue;
+        }
+        if (tid == 0 && g.brick_move) {              // rebuilt at the positions of this step head: the bound restarts
+            g.brick_move[bidx] = 0.f;
+            atomicAdd(&g.ctl->bricks_flagged, 1);
         }
         const Brick br = g.bricks[bidx];
         const int key0 = g.ckey[br.t0], key1 = g.ckey[br.t1 - 1];
@@ -405,6 +410,7 @@ __global__ void __launch_bounds__(BT) k_list_reorder(Ctl *ctl, const GridInfo *g
                                                      const int *__restrict__ nl_cnt, size_t nl_stride, int lcap) {
     if (ctl->error || ctl->done || !ctl->list_build || ctl->list_fail) return;
     const bool flagged_only = ctl->list_build == LIST_BUILD_FLAGGED;
+    if (flagged_only && ctl->bricks_urgent == 0) return;
     extern __shared__ __align__(16) unsigned short s_out[];   // [REORDER_MAX_SLOTS][BT], then the overflow scratch [REORDER_OVF_CAP][BT]
     unsigned short *const s_ovf = s_out + (size_t)REORDER_MAX_SLOTS * BT;
     __shared__ int s_brick;

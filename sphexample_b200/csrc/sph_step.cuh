@@ -117,6 +117,7 @@ __global__ void k_step_end(Ctl *ctl, const GridInfo *grid) {
         ctl->n_list_builds += 1;
     }
     ctl->bricks_flagged = 0;
+    ctl->bricks_urgent = 0;
     step_end(ctl);
 }
 

@@ -239,6 +239,7 @@ class Sim final : public sphb200_sim {
     int opt_list_reorder;                        // bank-aware entry order (sph_listorder.h, k_list_reorder)
     int opt_list_local;                          // per-brick list validity (brick_list_decision) instead of one global bound
     int opt_verify_lists = 0;                    // test hook: count listed-pair misses before every pass (k_list_verify)
+    int opt_list_lookahead = 3;                  // bricks due within this many steps are rebuilt along with the urgent ones
     DevBuf<float> vbox, brick_move;              // per-cell velocity boxes (2 buffers x 6 floats), per-brick displacement bounds
     DevBuf<int> brick_flag;
     double opt_skin;                             // list skin as a fraction of H
@@ -298,6 +299,7 @@ class Sim final : public sphb200_sim {
         opt_skin = env_int("SPHB200_SKIN_PCT", 4) * 0.01;       // r2q sweep with per-brick rebuilds: 3 % .. 10 % -> 871 / 874 / 867 / 858 / 848 / 818 Mpu/s
         opt_list_reorder = env_int("SPHB200_LIST_REORDER", 1);
         opt_list_local = env_int("SPHB200_LIST_LOCAL", 1);
+        opt_list_lookahead = env_int("SPHB200_LIST_LOOKAHEAD", 3);
         am.ax_s = D - 1;   // default: the reference's most significant axis
         am.ax_m = (D == 3) ? 1 : 0;
         build_phys();
@@ -398,6 +400,7 @@ class Sim final : public sphb200_sim {
         else if (k == "list_reorder") opt_list_reorder = (int)value;
         else if (k == "list_local") opt_list_local = (int)value;
         else if (k == "verify_lists") opt_verify_lists = (int)value;
+        else if (k == "list_lookahead") opt_list_lookahead = std::max(0, (int)value);
         else return fail(SPHB200_EINVAL, "unknown option '%s'", k.c_str());
         return SPHB200_OK;
     }
@@ -862,6 +865,7 @@ class Sim final : public sphb200_sim {
         g.list_cap_cand = list_cap_cand();
         g.list_reorder = opt_list_reorder;
         g.brick_flag = brick_flag.p;
+        g.brick_move = opt_list_local ? brick_move.p : nullptr;
         const double Hs = prm.H * (1.0 + opt_skin);
         g.Hs2 = (T)(Hs * Hs);
         g.force_cull = cull_force;
@@ -911,7 +915,7 @@ class Sim final : public sphb200_sim {
             const size_t bs = (size_t)(cell_cap + 8) * 6;
             k_cell_vbox<T, D><<<grid_for(cell_cap), 256, 0, stream>>>(B.p, cell_start.p, d_grid.p, d_ctl.p, vbox.p, bs);
             k_brick_bounds<D><<<num_sms * 8, 256, 0, stream>>>(d_ctl.p, d_grid.p, bricks.p, ckey.p, vbox.p, bs, brick_move.p,
-                                                                           brick_flag.p, opt_skin * prm.H);
+                                                                           brick_flag.p, opt_skin * prm.H, (double)opt_list_lookahead);
             launches += 2;
             CK(cudaGetLastError());
         }

@@ -181,7 +181,10 @@ extern "C" int shim_rainbow_order(const unsigned short *entries, int n_slots, in
 
 // per-brick list validity (brick_list_decision): returns 1 when the brick must be rebuilt; *move is updated
 extern "C" int shim_brick_decision(float *move, float D, double dt_prev, double dt2, double skin) {
-    return brick_list_decision(move, D, dt_prev, dt2, skin) ? 1 : 0;
+    // (as the kernels use it: a brick that must be rebuilt now has its bound reset by the build)
+    const int r = brick_list_decision(move, D, dt_prev, dt2, skin, 0.0);
+    if (r == 2) *move = 0.f;
+    return r == 2 ? 1 : 0;
 }
 
 // step-by-step variant of shim_control_trace for tests whose particle motion depends on the dt decided here
