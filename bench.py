@@ -401,6 +401,14 @@ def run_ours(args, rank, world, local_rank):
     k1 = names.index("05-07 First NeighborLoop + half step (fused)")
     k2 = names.index("08-11 Second NeighborLoop + full step (fused)")
     pass1_ms, pass2_ms = float(np.median(mat[:, k1])), float(np.median(mat[:, k2]))
+    per_rank = None
+    if world > 1:   # what every rank spends in its passes and owns: the load balance of the slab decomposition
+        t = torch.tensor([pass1_ms, pass2_ms, float(sim.report()["n_particles"]), float(sim.stat("list_entries"))],
+                         device="cuda", dtype=torch.float64)
+        allr = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        per_rank = {"pass1_ms": [round(float(a[0]), 4) for a in allr], "pass2_ms": [round(float(a[1]), 4) for a in allr],
+                    "owned": [int(a[2]) for a in allr], "list_entries_per_particle": [round(float(a[3]), 1) for a in allr]}
     pass1_ms, pass2_ms = max_over_ranks([pass1_ms, pass2_ms])
     n_local_max = int(max_over_ranks([sim.report()["n_particles"]])[0])
     list_entries = max_over_ranks([sim.stat("list_entries")])[0]
@@ -490,7 +498,7 @@ def run_ours(args, rank, world, local_rank):
             line["scaling_note"] = (f"weak scaling at {C4_PARTICLES // 8} particles per GPU for N >= 2 (N = 8 is C4); the N = 1 line is C3 "
                                     f"({C3_PARTICLES} particles), the configuration the metric is quoted on")
             line["slab"] = {"axis": "xyz"[SLAB_AXIS], "edges": [int(e) for e in dec.edges], "boundary_weight": dec.boundary_weight,
-                            "owned_max": n_local_max, "owned_mean": n / world, "halo_bytes_per_step": halo_bytes}
+                            "owned_max": n_local_max, "owned_mean": n / world, "halo_bytes_per_step": halo_bytes, "per_rank": per_rank}
             line["selfcheck"] = selfcheck
         # ---- CPU baseline (oracle port) on a bounded sample of the same workload, N = 1 only ----
         if world == 1:
