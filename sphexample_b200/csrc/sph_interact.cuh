@@ -50,6 +50,7 @@ struct InteractArgs {
     const typename L::TA *A;
     const typename L::TB *B;
     const T *RN;                       // ρₙ (pass 1: state-n density, Q2); unused in pass 0
+    T *rn_out;                         // pass 0, fused: where the epilogue leaves ρₙ of its particle (null: k_snapshot_rho did it)
     const typename L::TB *Bn;          // vₙ of neighbours (pass 1 + LaminarSPS only)
     // own state n, read and overwritten by the fused corrector (pass 1)
     typename L::TA *An_rw;
@@ -162,6 +163,7 @@ __device__ __forceinline__ void interact_epilogue(const InteractArgs<T, D> &g, i
             L::pack(oa, ob, xh, vh, ml > T(0) ? rhoh : -rhoh, eos_gamma7(ph, rhoh));
             g.Ah_out[i] = oa;
             g.Bh_out[i] = ob;
+            if (g.rn_out) g.rn_out[i] = rho_a;   // ρₙ for the pass-2 diffusion / viscosity terms (Q2): no separate snapshot sweep
         } else {
             // LimitDensityAtBoundary!(ρ) + DensityEpsi! + FullTimeStep + Pressure!  (S16-S18, S5)
             const T dt = (T)g.ctl->dt;

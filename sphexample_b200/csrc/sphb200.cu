@@ -247,6 +247,7 @@ class Sim final : public sphb200_sim {
     DevBuf<int> nl_cnt;
     size_t nl_stride = 0;
     int cull_force = 1;   // the cull kernel ignores ctl->list_mode (lists off / stage-level calls)
+    bool snapshot_in_epilogue = false;   // this step's ρₙ snapshot is taken by the pass-1 epilogue
     int brick_part = 0;   // which bricks the next interaction launches take: 0 all, 1 slab boundary, 2 interior
     unsigned *bnd_flag = nullptr;   // slab mode: flag the next interaction launches raise after their boundary bricks
     unsigned bnd_epoch = 0;
@@ -833,6 +834,7 @@ class Sim final : public sphb200_sim {
         g.A = pass ? Ah.p : A.p;
         g.B = pass ? Bh.p : B.p;
         g.RN = RN.p;
+        g.rn_out = (pass == 0 && epilogue == EPI_FUSED && snapshot_in_epilogue) ? RN.p : nullptr;
         g.Bn = B2.p;   // vₙ snapshot (LaminarSPS pass 2, Q2); B itself is rewritten by the fused corrector
         g.An_rw = A.p;
         g.Bn_rw = B.p;
@@ -998,10 +1000,15 @@ class Sim final : public sphb200_sim {
     }
 
     // state-n snapshots the pass-2 pair terms read (Q2): ρₙ always, vₙ for LaminarSPS
-    int enqueue_snapshots() {
-        k_snapshot_rho<T, D><<<grid_for(n), 256, 0, stream>>>(A.p, RN.p, (int)n, d_ctl.p);
-        ++launches;
-        CK(cudaGetLastError());
+    // fused: the pass-1 epilogue writes ρₙ of every particle it owns, so the sweep is only needed for
+    // the stage-level entry points and for the halo copies of slab mode
+    int enqueue_snapshots(bool fused_step = false) {
+        snapshot_in_epilogue = fused_step && !slab.active;
+        if (!snapshot_in_epilogue) {
+            k_snapshot_rho<T, D><<<grid_for(n), 256, 0, stream>>>(A.p, RN.p, (int)n, d_ctl.p);
+            ++launches;
+            CK(cudaGetLastError());
+        }
         if (prm.viscosity == SPHB200_VISC_LAMINAR_SPS)
             CK(cudaMemcpyAsync(B2.p, B.p, (size_t)n * sizeof(TB), cudaMemcpyDeviceToDevice, stream));
         return SPHB200_OK;
@@ -1043,7 +1050,7 @@ class Sim final : public sphb200_sim {
     int enqueue_body_pre(cudaEvent_t *ev = nullptr) {
         int rc;
         if ((rc = enqueue_motion(-1.0))) return rc;                           // S3  "Motion"
-        if ((rc = enqueue_snapshots())) return rc;
+        if ((rc = enqueue_snapshots(true))) return rc;
         if (ev) CK(cudaEventRecord(ev[2], stream));
         if (prm.mdbc && (rc = enqueue_mdbc())) return rc;                     // S6  "04 Apply MDBC before Half TimeStep"
         return SPHB200_OK;
