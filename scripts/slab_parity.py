@@ -78,13 +78,15 @@ if os.environ.get("SLAB_PARITY_QUICK"):   # a short smoke of the exchange / migr
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0)
-axes3 = (1, 2)
+axes3 = (0, 1, 2)     # x-slabs (rows along y), y-slabs, z-slabs
 for ax in axes3:
     run_case("dam_break_3d_dp0.02", lambda: util.case_3d_small("float64"), 60, ax, 1e-9, 1e-8)
     run_case("dam_break_3d_dp0.02", lambda: util.case_3d_small("float32"), 60, ax, 5e-3, 5e-3)
 # fast flow: many rebuilds and migrations across the slab faces
 run_case("dam_break_3d_dp0.02_fast", lambda: util.case_3d_small("float64"), 150, 1, 1e-7, 1e-6, vel_scale=3.0)
+run_case("dam_break_3d_dp0.02_fast_x", lambda: util.case_3d_small("float64"), 150, 0, 1e-7, 1e-6, vel_scale=3.0)
 run_case("dam_break_2d_dp0.02", lambda: util.case_c1("float64"), 100, 1, 1e-9, 1e-8)
+run_case("dam_break_2d_dp0.02_x", lambda: util.case_c1("float64"), 100, 0, 1e-9, 1e-8)
 if rank == 0:
     if out_path:
         os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)

@@ -20,10 +20,6 @@
 
 namespace sph {
 
-struct AxisMap {
-    int ax_m, ax_s;   // which position component is the m / s axis (x is always component 0)
-};
-
 // Which table entries take part in a rebuild (slab mode, sph_slab_impl.cuh).  Disabled: all of
 // [0, n).  Enabled: only [p0, p1) and [q0, n) are live, and a live particle whose slab coordinate
 // lies outside [keep_lo, keep_hi) is dropped (it has been handed to a neighbour rank).  Dropped
@@ -113,7 +109,7 @@ __global__ void k_grid_setup(Ctl *ctl, GridInfo *grid, AxisMap am, long long cel
         ext[k] = (int)e;
         grid->cmin[k] = grid->bb_min[k] - 1;
     }
-    int nx = ext[0];
+    int nx = ext[am.ax_f];
     int nm = (D == 3) ? ext[am.ax_m] : 1;
     int ns = ext[am.ax_s];
     long long ncell = (long long)nx * nm * ns;
@@ -152,7 +148,7 @@ __global__ void k_cell_count(const int *__restrict__ ccoord, int n, AxisMap am, 
                              int *__restrict__ cell_count) {
     if (ctl->error || ctl->done || !ctl->do_rebuild) return;
     const int nx = grid->nx, nm = grid->nm;
-    const int cx0 = grid->cmin[0], cm0 = (D == 3) ? grid->cmin[am.ax_m] : 0, cs0 = grid->cmin[am.ax_s];
+    const int cx0 = grid->cmin[am.ax_f], cm0 = (D == 3) ? grid->cmin[am.ax_m] : 0, cs0 = grid->cmin[am.ax_s];
     const int trash = grid->ncell;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (ccoord[(size_t)i * D] == DEAD_COORD) {
@@ -160,7 +156,7 @@ __global__ void k_cell_count(const int *__restrict__ ccoord, int n, AxisMap am, 
             slot_out[i] = atomicAdd(&cell_count[trash], 1);
             continue;
         }
-        int cx = ccoord[(size_t)i * D + 0] - cx0;
+        int cx = ccoord[(size_t)i * D + am.ax_f] - cx0;
         int cm = (D == 3) ? ccoord[(size_t)i * D + am.ax_m] - cm0 : 0;
         int cs = ccoord[(size_t)i * D + am.ax_s] - cs0;
         int key = (cs * nm + cm) * nx + cx;

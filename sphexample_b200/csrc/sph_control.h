@@ -71,6 +71,40 @@ struct GridInfo {
 };
 
 
+// Which position component plays which part in the cell key ((c_s nm + c_m) nf + c_f): f = fastest
+// (a row of cells runs along it), m = middle (3D only), s = slowest = the slab axis.  Default
+// f = x, m = y, s = z — the reference's own cell order.  The reference orders cells with the LAST
+// component most significant (CartesianIndex sort, src/SPHCellList.jl:142); that order decides the
+// density-diffusion roles (Q1), see row_role().
+struct AxisMap {
+    int ax_f, ax_m, ax_s;
+};
+
+// Roles of the pairs between a target's cell and the cells of one neighbouring row (offsets dm, ds
+// along the m / s axes).  *pre: decided by an axis that the reference compares BEFORE the fast axis
+// (+1: every cell of the row is lower than the target's cell, the target is "i"; -1: higher);
+// 0: the fast axis decides first, per candidate — a lower fast-axis cell is a lower cell — and for a
+// candidate in the target's own fast-axis column *post decides (0: same cell, the index order does).
+SPH_HD void row_role(const AxisMap &am, int D, int dm, int ds, int *pre, int *post) {
+    *pre = *post = 0;
+    // walk the components from most to least significant (D-1 .. 0)
+    bool before_f = true;
+    for (int k = D - 1; k >= 0; --k) {
+        if (k == am.ax_f) {
+            before_f = false;
+            continue;
+        }
+        const int off = (k == am.ax_s) ? ds : ((D == 3 && k == am.ax_m) ? dm : 0);
+        if (off == 0) continue;
+        if (before_f) {
+            if (*pre == 0) *pre = -off;
+        } else {
+            if (*post == 0) *post = -off;
+        }
+    }
+}
+
+
 #define SPH_ERR_EINVAL (-1)
 #define SPH_ERR_ECUDA (-2)
 #define SPH_ERR_ESTATE (-3)

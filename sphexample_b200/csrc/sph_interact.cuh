@@ -76,7 +76,7 @@ struct InteractArgs {
     int cap;                           // staged candidates per stage (multiple of 4)
     int epilogue;                      // EPI_STORE / EPI_FUSED
     int use_tma;                       // 1: cp.async.bulk staging, 0: cooperative ld/st staging
-    int ref_major_is_s;                // 1: slab axis is the reference's most significant axis
+    AxisMap am;                        // which component is the fast / middle / slab axis of the cell key (roles: row_role)
     int counter_slot;                  // which ctl->work_counter this launch consumes
     int brick_part;                    // 0: all bricks, 1: slab-boundary bricks, 2: interior bricks
     // slab mode, single launch per pass: the boundary-layer bricks [0, nbricks_bnd) are taken first;
@@ -425,11 +425,20 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
                     lo = g.cell_start[rk + cxi - 1];
                     hi = g.cell_start[rk + cxi + 2];
                 }
-                // role of the row: +1 b's row is lower in the reference's cell order
-                // (a is "i"), -1 higher (a is "j"), 0 same row (decided per candidate)
-                int major = g.ref_major_is_s ? ds : dm;
-                int minor = g.ref_major_is_s ? dm : ds;
-                int rowrole = major != 0 ? -major : -minor;
+                // role of the row (row_role): +1 every cell of the row is lower in the reference's
+                // cell order (a is "i"), -1 higher (a is "j"), 0: decided per candidate —
+                //   role = j < r_lim  and  unsigned(j - r_base) > r_thr
+                // the target's own row: b's cell is lower, or same cell and a < b (r_lim = ce_a, r_base = cs_a,
+                // r_thr = i - cs_a); a row the fast axis outranks: b's fast-axis cell is lower, or the same
+                // and the row's remaining offset says so (r_lim = r_base = start or end of that cell)
+                int rowrole, rowpost;
+                row_role(g.am, D, dm, ds, &rowrole, &rowpost);
+                int r_lim = ce_a, r_base = cs_a;
+                unsigned r_thr = (unsigned)(i - cs_a);
+                if (rowrole == 0 && (dm != 0 || ds != 0)) {
+                    r_lim = r_base = valid ? g.cell_start[rk + cxi + (rowpost > 0 ? 1 : 0)] : 0;
+                    r_thr = 0x7fffffffu;
+                }
                 // staged global index range of this row in this stage
                 const int jbase = s_w0a[r] - s_off[r];   // global j = staged position + jbase
                 int jb = lo_s + jbase, je = hi_s + jbase;
@@ -453,7 +462,6 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
                 auto cull = [&](auto same_row) {
                     constexpr bool SAME_ROW = decltype(same_row)::value;
                     const unsigned role_const = rowrole > 0 ? (unsigned)ROLE_BIT : 0u;
-                    const unsigned self_off = (unsigned)(i - cs_a);
                     for (int j4 = jb; j4 < je; j4 += 4) {
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -472,12 +480,10 @@ __global__ void __launch_bounds__(BT) k_interact(const InteractArgs<T, D> g) {
                             // where a term is non-zero at r = 0 (kernel sums of the generic path)
                             bool ok = (r2 <= H2) & ((unsigned)(j - lo) < wlen);
                             if (GENERIC) ok &= (j != i);
-                            // role bit: constant per row, except in the target's own
-                            // row where a is "i" iff b's cell is lower, or same cell and a < b:
-                            //   j in [lo, cs_a) or (i, ce_a)  <=>  j < ce_a and not cs_a <= j <= i
+                            // role bit: constant per row, or per candidate (see above)
                             unsigned code = (unsigned)(j + (sbase + (int)role_const));
                             if (SAME_ROW)
-                                code = (unsigned)sj | (((j < ce_a) & ((unsigned)(j - cs_a) > self_off)) ? (unsigned)ROLE_BIT : 0u);
+                                code = (unsigned)sj | (((j < r_lim) & ((unsigned)(j - r_base) > r_thr)) ? (unsigned)ROLE_BIT : 0u);
                             if (COMPACT) {
                                 // predicated append (no branch): store + pointer bump under `ok`
                                 asm volatile(

@@ -326,9 +326,14 @@ __global__ void __launch_bounds__(BT) k_list_build(const InteractArgs<T, D> g) {
                     lo = g.cell_start[rk + cxi - 1];
                     hi = g.cell_start[rk + cxi + 2];
                 }
-                int major = g.ref_major_is_s ? ds : dm;
-                int minor = g.ref_major_is_s ? dm : ds;
-                int rowrole = major != 0 ? -major : -minor;
+                int rowrole, rowpost;                        // roles: see k_interact / row_role
+                row_role(g.am, D, dm, ds, &rowrole, &rowpost);
+                int r_lim = ce_a, r_base = cs_a;
+                unsigned r_thr = (unsigned)(i - cs_a);
+                if (rowrole == 0 && (dm != 0 || ds != 0)) {
+                    r_lim = r_base = valid ? g.cell_start[rk + cxi + (rowpost > 0 ? 1 : 0)] : 0;
+                    r_thr = 0x7fffffffu;
+                }
                 const int jbase = s_w0a[r] - s_off[r];       // global j = window index + jbase
                 int jb = lo_s + jbase, je = hi_s + jbase;
                 int ulo = __shfl_sync(0xffffffffu, lo, 0);
@@ -342,7 +347,6 @@ __global__ void __launch_bounds__(BT) k_list_build(const InteractArgs<T, D> g) {
                 const int sbase = -jbase - s0;               // smem slot = j + sbase
                 const unsigned wlen = (unsigned)(hi - lo);
                 const unsigned role_const = rowrole > 0 ? (unsigned)ROLE_BIT : 0u;
-                const unsigned self_off = (unsigned)(i - cs_a);
                 // (two instantiations of the walk: the per-candidate role logic of the target's own row
                 //  costs 6 issue slots per candidate even when predicated off)
                 auto walk = [&](auto same_row_tag) {
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(BT) k_list_build(const InteractArgs<T, D> g) {
                             if (GENERIC) ok &= (j != i);
                             unsigned code = (unsigned)(j + (int)(role_const - (unsigned)jbase));
                             if (SAME_ROW)
-                                code = (unsigned)(j - jbase) | (((j < ce_a) & ((unsigned)(j - cs_a) > self_off)) ? (unsigned)ROLE_BIT : 0u);
+                                code = (unsigned)(j - jbase) | (((j < r_lim) & ((unsigned)(j - r_base) > r_thr)) ? (unsigned)ROLE_BIT : 0u);
                             asm volatile(
                                 "{\n\t.reg .pred p;\n\t"
                                 "setp.ne.u32 p, %2, 0;\n\t"

@@ -49,9 +49,7 @@ namespace {
 template <class T, int D>
 int Sim<T, D>::comm_init(const uint8_t *uid, int rank, int world, int axis) {
     if (!uid || world < 1 || rank < 0 || rank >= world) return fail(SPHB200_EINVAL, "comm_init: bad rank/world");
-    if (axis < 1 || axis >= D)
-        return fail(SPHB200_EINVAL, "comm_init: the slab axis must be 1..%d (x is the fastest key component: a cell row "
-                                    "must stay on one rank)", D - 1);
+    if (axis < 0 || axis >= D) return fail(SPHB200_EINVAL, "comm_init: the slab axis must be 0..%d", D - 1);
     if (prm.mdbc) return fail(SPHB200_EINVAL, "comm_init: SimpleMDBC is single-GPU only (ghost nodes reach two cells across a slab face)");
     if (slab.active) return fail(SPHB200_ESTATE, "comm_init: communicator already initialised");
     if (uploaded) return fail(SPHB200_ESTATE, "comm_init must precede upload");
@@ -88,9 +86,16 @@ int Sim<T, D>::comm_init(const uint8_t *uid, int rank, int world, int axis) {
     }
     CKS(cudaMalloc((void **)&slab.d_counts, 8 * sizeof(int)));
     CKS(cudaMallocHost((void **)&slab.h_counts, 8 * sizeof(int)));
+    // the slab axis is the slowest key component (a slab layer is one contiguous range of the table); of the
+    // other axes the lower component stays the fastest (x, or y when the slabs are cut along x)
     am.ax_s = axis;
-    am.ax_m = (D == 3) ? (axis == 1 ? 2 : 1) : 0;
-    ref_major_is_s = (D == 2) || (am.ax_s > am.ax_m);
+    if (D == 3) {
+        am.ax_f = axis == 0 ? 1 : 0;
+        am.ax_m = axis == 2 ? 1 : 2;
+    } else {
+        am.ax_f = axis == 0 ? 1 : 0;
+        am.ax_m = am.ax_f;
+    }
     slab.active = true;
     return SPHB200_OK;
 }

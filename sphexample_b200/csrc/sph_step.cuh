@@ -284,7 +284,7 @@ __global__ void k_mdbc_gather(const typename Lay<T, D>::TA *__restrict__ A, cons
         int gc[3] = {0, 0, 0};
 #pragma unroll
         for (int k = 0; k < D; ++k) gc[k] = map_floor_dev((double)gp[k], inv_cutoff, bad);
-        int cx = gc[0] - grid->cmin[0];
+        int cx = gc[am.ax_f] - grid->cmin[am.ax_f];
         int cm = (D == 3) ? gc[am.ax_m] - grid->cmin[am.ax_m] : 0;
         int cs = gc[am.ax_s] - grid->cmin[am.ax_s];
         double bv[E], Am[E][E];

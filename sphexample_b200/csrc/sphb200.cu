@@ -253,7 +253,6 @@ class Sim final : public sphb200_sim {
     unsigned bnd_epoch = 0;
     bool generic = false;
     AxisMap am;
-    int ref_major_is_s = 1;
     int own_lo = INT_MIN, own_hi = INT_MAX;
     // particle table (cell-sorted) and scratch copy for the reorder
     DevBuf<TA> A, A2, Ah;
@@ -301,7 +300,8 @@ class Sim final : public sphb200_sim {
         opt_list_reorder = env_int("SPHB200_LIST_REORDER", 1);
         opt_list_local = env_int("SPHB200_LIST_LOCAL", 1);
         opt_list_lookahead = env_int("SPHB200_LIST_LOOKAHEAD", 3);
-        am.ax_s = D - 1;   // default: the reference's most significant axis
+        am.ax_f = 0;       // default: the reference's own cell order (x fastest, last component most significant)
+        am.ax_s = D - 1;
         am.ax_m = (D == 3) ? 1 : 0;
         build_phys();
     }
@@ -663,7 +663,7 @@ class Sim final : public sphb200_sim {
         int cx = key % h_grid->nx;
         int r = key / h_grid->nx;
         int cm = r % h_grid->nm, cs = r / h_grid->nm;
-        c[0] = cx + h_grid->cmin[0];
+        c[am.ax_f] = cx + h_grid->cmin[am.ax_f];
         if (D == 3) c[am.ax_m] = cm + h_grid->cmin[am.ax_m];
         c[am.ax_s] = cs + h_grid->cmin[am.ax_s];
     }
@@ -855,7 +855,7 @@ class Sim final : public sphb200_sim {
         g.phys = ph;
         g.epilogue = epilogue;
         g.use_tma = opt_tma;
-        g.ref_major_is_s = ref_major_is_s;
+        g.am = am;
         g.counter_slot = pass * 3 + brick_part;
         g.brick_part = brick_part;
         g.bnd_flag = bnd_flag;
@@ -1389,7 +1389,7 @@ class Sim final : public sphb200_sim {
                 o.e = cs[key + 1];
                 occ.push_back(o);
             }
-        if (!ref_major_is_s)
+        if (!(am.ax_f == 0 && am.ax_s == D - 1))   // the device key order is not the reference's
             std::stable_sort(occ.begin(), occ.end(), [](const Occ &a, const Occ &b) {
                 for (int k = D - 1; k >= 0; --k)
                     if (a.c[k] != b.c[k]) return a.c[k] < b.c[k];

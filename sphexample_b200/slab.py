@@ -76,8 +76,9 @@ def slab_bounds(edges: Sequence[int], rank: int):
 
 
 def best_axis(positions: np.ndarray, H_inv: float, world: int) -> int:
-    """Slab axis among 1..D-1 (x stays the fastest key component): the one whose balanced split
-    has the smallest halo, i.e. the most layers per rank."""
+    """Default slab axis: among y (and z) the one with the most cell layers.  x is accepted too
+    (pass axis=0; the rows of cells then run along y), but a flow that runs along x — a dam break —
+    keeps re-distributing particles along it, while a y split stays balanced through the run."""
     D = positions.shape[1]
     best, best_layers = 1, -1
     for ax in range(1, D):
