@@ -125,11 +125,21 @@ __device__ __forceinline__ void signal_boundary_brick(const InteractArgs<T, D> &
     }
 }
 
+// What the fused epilogue reads of its own particle, loaded at the START of the particle's work by
+// the list kernel (at the end it would be an exposed memory round trip per 32-target sub-brick).
+template <class T, int D>
+struct EpiloguePrefetch {
+    typename Lay<T, D>::TA an;   // own state n (pass 2 only)
+    typename Lay<T, D>::TB bn;
+    uint8_t type;
+};
+
 // Per-particle tail of a pass: plain stores (stage-level entry points) or the fused symplectic
 // half / full update, shared by the cull kernel and the list kernel.
 template <class T, int D, int PASS, bool GENERIC>
 __device__ __forceinline__ void interact_epilogue(const InteractArgs<T, D> &g, int i, const T *xa, const T *va, T rho_a,
-                                                  const PairAccum<T, D> &sacc, T drho, T *acc, StepRed<T> &red) {
+                                                  const PairAccum<T, D> &sacc, T drho, T *acc, StepRed<T> &red,
+                                                  const EpiloguePrefetch<T, D> *pre = nullptr) {
     using L = Lay<T, D>;
     using TA = typename L::TA;
     using TB = typename L::TB;
@@ -151,7 +161,7 @@ __device__ __forceinline__ void interact_epilogue(const InteractArgs<T, D> &g, i
         g.drhodt[i] = drho;
         g.acc[i] = L::mkv(acc);
     } else {
-        const uint8_t ty = g.type[i];
+        const uint8_t ty = pre ? pre->type : g.type[i];
         const T gf = (T)type_gf(ty), ml = (T)type_ml(ty);
         if (PASS == 0) {
             // HalfTimeStep + LimitDensityAtBoundary!(ρₙ⁺) + Pressure!(ρₙ⁺)  (S9, S10, S13)
@@ -168,7 +178,8 @@ __device__ __forceinline__ void interact_epilogue(const InteractArgs<T, D> &g, i
             // LimitDensityAtBoundary!(ρ) + DensityEpsi! + FullTimeStep + Pressure!  (S16-S18, S5)
             const T dt = (T)g.ctl->dt;
             T xn[D], vn[D], rs, Pn;
-            L::unpack(g.An_rw[i], g.Bn_rw[i], xn, vn, rs, Pn);
+            if (pre) L::unpack(pre->an, pre->bn, xn, vn, rs, Pn);
+            else L::unpack(g.An_rw[i], g.Bn_rw[i], xn, vn, rs, Pn);
             T rho = sph_abs(rs);
             T gc[D];
 #pragma unroll

@@ -901,6 +901,8 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
 #pragma unroll
             for (int k = 0; k < D; ++k) xa[k] = va[k] = T(0);
             int nchunk = 0;
+            EpiloguePrefetch<T, D> epf;
+            epf.type = 0;
             if (valid) {
                 T rs;
                 L::unpack(g.A[i], g.B[i], xa, va, rs, P_a);
@@ -908,6 +910,13 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
                 ml_a = rs > T(0) ? T(1) : T(0);
                 rhon_a = PASS ? g.RN[i] : rho_a;
                 nchunk = g.nl_cnt[i] >> 3;
+                if (g.epilogue == EPI_FUSED) {
+                    epf.type = g.type[i];
+                    if (PASS) {
+                        epf.an = g.An_rw[i];
+                        epf.bn = g.Bn_rw[i];
+                    }
+                }
             }
             // List chunks are prefetched LIST_PF chunks ahead: LIST_PF register buffers, each with its
             // own loop-carried pointer, and the chunk loop unrolled LIST_PF times so that no buffer is
@@ -1058,7 +1067,7 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
             for (int k = 0; k < D; ++k) acc[k] = T(0);
             if constexpr (PACKED) fast_finish2<D>(ft, fs2, drho, acc);
             else if (!GENERIC) fast_finish<T, D>(ft, fs, drho, acc);
-            if (valid) interact_epilogue<T, D, PASS, GENERIC>(g, i, xa, va, rho_a, sacc, drho, acc, red);
+            if (valid) interact_epilogue<T, D, PASS, GENERIC>(g, i, xa, va, rho_a, sacc, drho, acc, red, g.epilogue == EPI_FUSED ? &epf : nullptr);
 
             if (bidx < nbnd) {
                 // slab mode: the warp that retires the last sub-brick of the last boundary brick
