@@ -181,8 +181,10 @@ def run_reference(args, rank, world):
     orc.build()
     threads = host_threads()
     budget_s = float(os.environ.get("SPHB200_REF_BUDGET_S", "100"))
-    n_full = int(args.particles) if args.particles else workload_particles(args.gpus)
-    n_case = min(n_full, int(os.environ.get("SPHB200_REF_MAX_PARTICLES", "2100000")))
+    from sphexample_b200 import cases
+    n_target = int(args.particles) if args.particles else workload_particles(args.gpus)
+    n_full = cases.dam_break_3d_count(cases.dp_for_count_3d(n_target))     # the lattice's actual particle count (as the GPU arm reports)
+    n_case = min(n_target, int(os.environ.get("SPHB200_REF_MAX_PARTICLES", "2100000")))
     case, dp = build_case(n_case, "float64")
     state, how = None, "at rest (no GPU to develop the flow)"
     try:
@@ -196,7 +198,7 @@ def run_reference(args, rank, world):
     value, k, secs = cpu_rate(case, particles, threads, args.steps, args.warmup, budget_s)
     n = len(particles)
     sample = (f"{k} of the {args.steps} steps, {n} particles (dp={dp:.6f})"
-              + ("" if n_case == n_full else f" = a smaller lattice of the same case standing in for the {n_full}-particle workload")
+              + ("" if n_case == n_target else f" = a smaller lattice of the same case standing in for the {n_full}-particle workload")
               + f", state {how}, fp64, {secs:.1f} s on {threads} host threads")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * n_full / (value * 1e6), "higher_is_better": True, "scaling": "weak",
