@@ -366,13 +366,20 @@ __global__ void k_mdbc_gather(const typename Lay<T, D>::TA *__restrict__ A, cons
 
 template <class T, int D>
 __global__ void k_mdbc_apply(typename Lay<T, D>::TA *A, T *RN, const uint8_t *__restrict__ type,
-                             const T *__restrict__ rho_new, const uint8_t *__restrict__ has_new, int n, const Ctl *ctl) {
+                             const T *__restrict__ rho_new, const uint8_t *__restrict__ has_new, int n, Ctl *ctl) {
     using L = Lay<T, D>;
     if (ctl->error || ctl->done) return;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (!has_new[i]) continue;
         typename L::TA a = A[i];
         T r = rho_new[i];
+        // The table carries the MotionLimiter in the SIGN of the stored density, so a density must be
+        // positive.  The reference would write a zero or negative extrapolation as it is (and go on with
+        // it); that cannot be represented here — and is not physical — so it stops the run instead.
+        if (!(r > T(0))) {
+            atomicCAS(&ctl->error, 0, SPH_ERR_ENUMERIC);
+            continue;
+        }
         L::set_rhos(a, type[i] == 1 ? r : -r);
         A[i] = a;
         RN[i] = r;

@@ -40,3 +40,53 @@ def write_particles_csv(path: str, state: dict, select=None) -> int:
         for k in range(len(idp)):
             w.writerow([int(idp[k]), *map(float, vel[k]), float(rho[k]), float(prs[k]), int(typ[k]), int(mk[k]), *map(float, pos[k])])
     return int(len(idp))
+
+
+def write_particles_vtp(path: str, state: dict, select=None) -> int:
+    """Write a `Simulation.download()` state as a VTK XML PolyData file (.vtp, binary "appended raw"
+    data) that ParaView opens directly: one vertex per particle, point data Velocity, Acceleration
+    (when present), Density, Pressure, ID, Type, GroupMarker — the variables the reference's VTKHDF
+    writer exports by default (src/ProduceHDFVTK.jl:461-621).  This is NOT the reference's VTKHDF
+    container (no HDF5 library is available in this image); it is the same data in the other file
+    format ParaView reads natively.  Returns the number of points."""
+    import struct
+    sel = slice(None) if select is None else select
+    pos = _xyz(state["Position"][sel]).astype("<f4")
+    n = int(pos.shape[0])
+    arrays = [("Velocity", _xyz(state["Velocity"][sel]).astype("<f4"), "Float32", 3)]
+    if "Acceleration" in state:
+        arrays.append(("Acceleration", _xyz(state["Acceleration"][sel]).astype("<f4"), "Float32", 3))
+    arrays.append(("Density", np.asarray(state["Density"][sel]).astype("<f4"), "Float32", 1))
+    if "Pressure" in state:
+        arrays.append(("Pressure", np.asarray(state["Pressure"][sel]).astype("<f4"), "Float32", 1))
+    for name, typ, vtk in (("ID", "<i8", "Int64"), ("Type", "u1", "UInt8"), ("GroupMarker", "<u8", "UInt64")):
+        if name in state:
+            arrays.append((name, np.asarray(state[name][sel]).astype(typ), vtk, 1))
+    conn = np.arange(n, dtype="<i8")
+    offs = np.arange(1, n + 1, dtype="<i8")
+    blobs, offset = [], 0
+
+    def add(a):
+        nonlocal offset
+        raw = np.ascontiguousarray(a).tobytes()
+        blobs.append(struct.pack("<Q", len(raw)) + raw)
+        o = offset
+        offset += 8 + len(raw)
+        return o
+    xml = ['<?xml version="1.0"?>',
+           '<VTKFile type="PolyData" version="1.0" byte_order="LittleEndian" header_type="UInt64">', "<PolyData>",
+           f'<Piece NumberOfPoints="{n}" NumberOfVerts="{n}" NumberOfLines="0" NumberOfStrips="0" NumberOfPolys="0">',
+           "<PointData>"]
+    for name, a, vtk, nc in arrays:
+        xml.append(f'<DataArray type="{vtk}" Name="{name}" NumberOfComponents="{nc}" format="appended" offset="{add(a)}"/>')
+    xml += ["</PointData>", "<Points>",
+            f'<DataArray type="Float32" Name="Points" NumberOfComponents="3" format="appended" offset="{add(pos)}"/>', "</Points>",
+            "<Verts>", f'<DataArray type="Int64" Name="connectivity" format="appended" offset="{add(conn)}"/>',
+            f'<DataArray type="Int64" Name="offsets" format="appended" offset="{add(offs)}"/>', "</Verts>", "</Piece>", "</PolyData>",
+            '<AppendedData encoding="raw">']
+    with open(path, "wb") as fh:
+        fh.write(("\n".join(xml) + "\n_").encode())
+        for b in blobs:
+            fh.write(b)
+        fh.write(b"\n</AppendedData>\n</VTKFile>\n")
+    return n
