@@ -404,21 +404,20 @@ __global__ void __launch_bounds__(BT) k_list_build(const InteractArgs<T, D> g) {
 // every half-word extraction is static, and the global loads prefetched two chunks ahead).
 // One thread per particle, a CTA per brick (the lane phase of a particle is its index in the brick,
 // mod 8); the reordered list is assembled in shared memory (out[chunk][slot][thread]) and leaves as
-// 16-byte stores.  Lists longer than REORDER_MAX_SLOTS, or with more than REORDER_OVF_CAP entries in
+// 16-byte stores.  Lists longer than max_slots (option reorder_slots), or with more than REORDER_OVF_CAP entries in
 // over-full bank groups, stay as built (valid, only slower).  Runs right after k_list_build.
 // =================================================================================================
 constexpr int REORDER_OVF_CAP = 32;
-constexpr int REORDER_MAX_SLOTS = 288;
 
 template <int BT>
 __global__ void __launch_bounds__(BT) k_list_reorder(Ctl *ctl, const GridInfo *grid, const Brick *__restrict__ bricks,
                                                      const int *__restrict__ brick_flag, unsigned sentinel_base, uint4 *nl,
-                                                     const int *__restrict__ nl_cnt, size_t nl_stride, int lcap) {
+                                                     const int *__restrict__ nl_cnt, size_t nl_stride, int lcap, int max_slots) {
     if (ctl->error || ctl->done || !ctl->list_build || ctl->list_fail) return;
     const bool flagged_only = ctl->list_build == LIST_BUILD_FLAGGED;
     if (flagged_only && ctl->bricks_urgent == 0) return;
-    extern __shared__ __align__(16) unsigned short s_out[];   // [REORDER_MAX_SLOTS][BT], then the overflow scratch [REORDER_OVF_CAP][BT]
-    unsigned short *const s_ovf = s_out + (size_t)REORDER_MAX_SLOTS * BT;
+    extern __shared__ __align__(16) unsigned short s_out[];   // [max_slots][BT], then the overflow scratch [REORDER_OVF_CAP][BT]
+    unsigned short *const s_ovf = s_out + (size_t)max_slots * BT;
     __shared__ int s_brick;
     const int tid = threadIdx.x;
     const int nbricks = grid->nbricks;
@@ -433,7 +432,7 @@ __global__ void __launch_bounds__(BT) k_list_reorder(Ctl *ctl, const GridInfo *g
         const unsigned total8 = sentinel_base;   // window indices >= this are sentinels / padding
         for (int i = br.t0 + tid; i < br.t1; i += BT) {
             const int n_slots = min(nl_cnt[i], lcap);
-            if (n_slots > REORDER_MAX_SLOTS) continue;
+            if (n_slots > max_slots) continue;
             const int nc = n_slots >> 3;
             const unsigned q = (unsigned)(i - br.t0) & 7u;
             uint4 *const lp = nl + i;

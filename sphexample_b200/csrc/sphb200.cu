@@ -240,6 +240,8 @@ class Sim final : public sphb200_sim {
     int opt_list_local;                          // per-brick list validity (brick_list_decision) instead of one global bound
     int opt_verify_lists = 0;                    // test hook: count listed-pair misses before every pass (k_list_verify)
     int opt_list_lookahead = 3;                  // bricks due within this many steps are rebuilt along with the urgent ones
+    int opt_build_smem_kb = 10;                  // staged positions per stage of k_list_build (r3b: 8-14 KB -> 2.76-2.80 ms first step, 24 KB 2.99)
+    int opt_reorder_slots = 224;                 // longest list k_list_reorder handles (its shared memory: (slots + 32) * 256 B per CTA)
     DevBuf<float> vbox, brick_move;              // per-cell velocity boxes (2 buffers x 6 floats), per-brick displacement bounds
     DevBuf<int> brick_flag;
     double opt_skin;                             // list skin as a fraction of H
@@ -402,6 +404,8 @@ class Sim final : public sphb200_sim {
         else if (k == "list_local") opt_list_local = (int)value;
         else if (k == "verify_lists") opt_verify_lists = (int)value;
         else if (k == "list_lookahead") opt_list_lookahead = std::max(0, (int)value);
+        else if (k == "build_smem_kb") opt_build_smem_kb = std::max(8, (int)value);
+        else if (k == "reorder_slots") opt_reorder_slots = std::max(64, ((int)value + 7) & ~7);
         else return fail(SPHB200_EINVAL, "unknown option '%s'", k.c_str());
         return SPHB200_OK;
     }
@@ -923,7 +927,7 @@ class Sim final : public sphb200_sim {
         }
         auto kern = k_list_build<T, D, GEN, BT>;
         const int list_bytes = LIST_CAP * BT * 2;   // append buffer
-        int smem = std::min(opt_smem_kb, 200) * 1024;
+        int smem = std::min(opt_build_smem_kb, 200) * 1024;
         int cap = std::min(((smem - 64) / (int)sizeof(TA)) & ~3, 32764);
         smem = cap * (int)sizeof(TA) + list_bytes;
         int ctas = 0, rc;
@@ -936,10 +940,10 @@ class Sim final : public sphb200_sim {
         CK(cudaGetLastError());
         if (opt_list_reorder) {
             auto rk = k_list_reorder<BT>;
-            const int rsmem = (REORDER_MAX_SLOTS + REORDER_OVF_CAP) * BT * 2;
+            const int rsmem = (opt_reorder_slots + REORDER_OVF_CAP) * BT * 2;
             if ((rc = configure_kernel(rk, BT, rsmem, &ctas))) return rc;
             rk<<<persistent_blocks(ctas), BT, rsmem, stream>>>(d_ctl.p, d_grid.p, bricks.p, brick_flag.p, (unsigned)(list_cap_cand() - 8), nl.p,
-                                                             nl_cnt.p, nl_stride, opt_lcap);
+                                                             nl_cnt.p, nl_stride, opt_lcap, opt_reorder_slots);
             ++launches;
             CK(cudaGetLastError());
         }
