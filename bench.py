@@ -294,10 +294,11 @@ def run_ours(args, rank, world, local_rank):
     dec = None
     if world > 1 or os.environ.get("SPHB200_BENCH_FORCE_SLAB"):   # (world of one: the slab code path without neighbours)
         from sphexample_b200 import slab
-        # slab edges: minimise the largest slab load; a wall particle counts half a fluid particle (most wall
-        # particles of this tank have no fluid neighbour at all, so their neighbour lists are short)
+        # slab edges: minimise the largest slab load; a wall particle counts 0.8 of a fluid particle — measured
+        # on C4 (profiles/r3d_bench_8gpu_c4.json, per_rank): the two end ranks, which own the side walls, spend
+        # 0.42 us per owned particle and pass against 0.45 for the interior ranks
         dec = slab.SlabDecomposition(sim, parts, p.H_inv, rank, world, axis=SLAB_AXIS,
-                                     boundary_weight=float(os.environ.get("SPHB200_BOUNDARY_WEIGHT", "0.5")))
+                                     boundary_weight=float(os.environ.get("SPHB200_BOUNDARY_WEIGHT", "0.8")))
         dec.join()
         mine = dec.mine
     else:
