@@ -215,6 +215,14 @@ int sphb200_comm_unique_id(uint8_t id_out[128]);
 int sphb200_comm_init(sphb200_sim *sim, const uint8_t id[128], int rank, int world_size, int axis);
 /* slab bounds of this rank along `axis`: owns cell coordinates lo <= c < hi (INT64_MIN/MAX = open) */
 int sphb200_set_slab(sphb200_sim *sim, int64_t cell_lo, int64_t cell_hi);
+/* SimpleMDBC across slabs (ApplyMDBCBeforeHalf!, src/SPHCellList.jl:219-266,491-505,598-622): the
+ * GhostPoints column as a global, static table — every rank passes the SAME table, ghost_points[ng][D]
+ * (nonzero entries of SimParticles.GhostPoints) and the IDs of their particles, strictly ascending.
+ * A ghost node is solved by the rank that owns the node's cell and the solves are all-reduced, so
+ * it does not matter how far across a slab face the node lies from its particle.  Call after
+ * comm_init; replaces the ghost_points argument of upload, which slab mode ignores. */
+int sphb200_set_ghost_nodes(sphb200_sim *sim, int64_t ng, const void *ghost_points,
+                            const int64_t *particle_ids);
 /* per-cell-column particle histogram along the slab axis (for balanced slab edges):
  * counts[c - *cell_min] for c in [*cell_min, *cell_min + *n_columns) */
 int sphb200_column_histogram(sphb200_sim *sim, int axis, int64_t *cell_min, int64_t *n_columns,

@@ -78,6 +78,25 @@ if os.environ.get("SLAB_PARITY_QUICK"):   # a short smoke of the exchange / migr
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0)
+def mdbc_cases():
+    # C5 (StillWedge, SimpleMDBC): ghost nodes lie up to two cells from their particles, across the faces
+    run_case("still_wedge_mdbc_2d_z", lambda: util.case_c5("float64"), 80, 1, 1e-9, 1e-7)
+    run_case("still_wedge_mdbc_2d_x", lambda: util.case_c5("float64"), 80, 0, 1e-9, 1e-7)
+    run_case("still_wedge_mdbc_2d_x_fast", lambda: util.case_c5("float64"), 150, 0, 1e-8, 1e-6, vel_scale=3.0)
+
+
+if os.environ.get("SLAB_PARITY_ONLY") == "mdbc":
+    mdbc_cases()
+    if rank == 0:
+        if out_path:
+            os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
+            with open(out_path, "w") as fh:
+                for r in lines:
+                    fh.write(json.dumps(r) + "\n")
+        print("SLAB PARITY", "OK" if lines and all(r["ok"] for r in lines) else "FAILED", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0)
 axes3 = (0, 1, 2)     # x-slabs (rows along y), y-slabs, z-slabs
 for ax in axes3:
     run_case("dam_break_3d_dp0.02", lambda: util.case_3d_small("float64"), 60, ax, 1e-9, 1e-8)
@@ -87,6 +106,7 @@ run_case("dam_break_3d_dp0.02_fast", lambda: util.case_3d_small("float64"), 150,
 run_case("dam_break_3d_dp0.02_fast_x", lambda: util.case_3d_small("float64"), 150, 0, 1e-7, 1e-6, vel_scale=3.0)
 run_case("dam_break_2d_dp0.02", lambda: util.case_c1("float64"), 100, 1, 1e-9, 1e-8)
 run_case("dam_break_2d_dp0.02_x", lambda: util.case_c1("float64"), 100, 0, 1e-9, 1e-8)
+mdbc_cases()
 if rank == 0:
     if out_path:
         os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)

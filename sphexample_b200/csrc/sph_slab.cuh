@@ -34,7 +34,7 @@ struct Comm;
 typedef Comm *comm_t;
 struct UniqueId { char internal[128]; };
 enum { Success = 0 };
-enum { Int8 = 0, Int32 = 2, Uint64 = 5 };   // ncclDataType_t values used here
+enum { Int8 = 0, Int32 = 2, Uint64 = 5, Float64 = 8 };   // ncclDataType_t values used here
 enum { Sum = 0, Max = 2 };                  // ncclRedOp_t
 
 struct Api {

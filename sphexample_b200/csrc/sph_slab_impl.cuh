@@ -50,7 +50,6 @@ template <class T, int D>
 int Sim<T, D>::comm_init(const uint8_t *uid, int rank, int world, int axis) {
     if (!uid || world < 1 || rank < 0 || rank >= world) return fail(SPHB200_EINVAL, "comm_init: bad rank/world");
     if (axis < 0 || axis >= D) return fail(SPHB200_EINVAL, "comm_init: the slab axis must be 0..%d", D - 1);
-    if (prm.mdbc) return fail(SPHB200_EINVAL, "comm_init: SimpleMDBC is single-GPU only (ghost nodes reach two cells across a slab face)");
     if (slab.active) return fail(SPHB200_ESTATE, "comm_init: communicator already initialised");
     if (uploaded) return fail(SPHB200_ESTATE, "comm_init must precede upload");
     CKS(cudaSetDevice(device));
@@ -108,6 +107,53 @@ int Sim<T, D>::set_slab(int64_t lo, int64_t hi) {
     own_hi = hi >= (int64_t)INT_MAX ? INT_MAX : (int)hi;
     if (slab.left < 0) own_lo = INT_MIN;
     if (slab.right < 0) own_hi = INT_MAX;
+    return SPHB200_OK;
+}
+
+// SimpleMDBC across slabs: the global, static ghost-node table (k_mdbc_nodes, sph_step.cuh).  Every rank
+// passes the same table: points[ng][D] of T and the IDs of the particles the nodes belong to, ascending.
+template <class T, int D>
+int Sim<T, D>::set_ghost_nodes(int64_t ng, const void *points, const int64_t *ids) {
+    if (!slab.active) return fail(SPHB200_ESTATE, "set_ghost_nodes is the slab-mode form of the ghost columns: call comm_init first (one GPU: pass ghost_points to upload)");
+    if (!prm.mdbc) return fail(SPHB200_EINVAL, "set_ghost_nodes: the handle was created with NoMDBC");
+    if (ng < 0 || ng > (int64_t)INT_MAX / 8 || (ng > 0 && (!points || !ids))) return fail(SPHB200_EINVAL, "set_ghost_nodes: bad arguments");
+    for (int64_t g = 1; g < ng; ++g)
+        if (ids[g] <= ids[g - 1]) return fail(SPHB200_EINVAL, "set_ghost_nodes: particle IDs must be strictly ascending (entry %lld)", (long long)g);
+    CKS(cudaSetDevice(device));
+    CKS(cudaStreamSynchronize(stream));
+    CKS(g_point.alloc((size_t)ng + 1));
+    CKS(g_id.alloc((size_t)ng + 1));
+    CKS(g_sol.alloc((size_t)ng * (D + 2) + 1));
+    if (ng > 0) {
+        std::vector<TV> hp((size_t)ng);
+        const T *src = (const T *)points;
+        memset(hp.data(), 0, hp.size() * sizeof(TV));
+        for (int64_t g = 0; g < ng; ++g)
+            for (int k = 0; k < D; ++k) ((T *)&hp[(size_t)g])[k] = src[(size_t)g * D + k];   // TV = D (2D) or 4 (3D) packed T
+        CKS(cudaMemcpyAsync(g_point.p, hp.data(), (size_t)ng * sizeof(TV), cudaMemcpyHostToDevice, stream));
+        CKS(cudaMemcpyAsync(g_id.p, ids, (size_t)ng * sizeof(long long), cudaMemcpyHostToDevice, stream));
+        CKS(cudaStreamSynchronize(stream));
+    }
+    n_ghost_nodes = (int)ng;
+    return SPHB200_OK;
+}
+
+// S6 in slab mode: solve the nodes whose cell this rank owns, all-reduce the solves, extrapolate to
+// every particle held here (owned and halo copies alike)
+template <class T, int D>
+int Sim<T, D>::slab_enqueue_mdbc() {
+    if (n_ghost_nodes < 0) return fail(SPHB200_ESTATE, "SimpleMDBC in slab mode needs the ghost-node table (sphb200_set_ghost_nodes) before the first step");
+    const int ng = n_ghost_nodes;
+    if (ng == 0) return SPHB200_OK;
+    k_mdbc_nodes<T, D><<<grid_for(ng, 128), 128, 0, stream>>>(A.p, g_point.p, ng, type.p, cell_start.p, d_grid.p, am, ph, prm.H_inv,
+                                                              own_lo, own_hi, g_sol.p, d_ctl.p);
+    ++launches;
+    CKS(cudaGetLastError());
+    NCK(nccl::api().AllReduce(g_sol.p, g_sol.p, (size_t)ng * (D + 2), nccl::Float64, nccl::Sum, slab.comm, stream));
+    k_mdbc_apply_nodes<T, D><<<grid_for(n), 256, 0, stream>>>(A.p, RN.p, type.p, id.p, (int)n, g_point.p, g_id.p, ng, g_sol.p, ph.rho0,
+                                                              d_ctl.p);
+    ++launches;
+    CKS(cudaGetLastError());
     return SPHB200_OK;
 }
 
@@ -392,6 +438,7 @@ int Sim<T, D>::slab_step_body(cudaEvent_t *ev, bool host_synced, cudaEvent_t *xe
     if ((rc = enqueue_motion(-1.0))) return rc;                       // S3
     if ((rc = enqueue_snapshots())) return rc;
     EV(2);
+    if (prm.mdbc && (rc = slab_enqueue_mdbc())) return rc;            // S6
     EV(3);
     if ((rc = enqueue_list_build())) return rc;
     EV(4);

@@ -263,6 +263,100 @@ __global__ void k_full_step(typename Lay<T, D>::TA *A, typename Lay<T, D>::TB *B
 // Two phases like the reference: new densities go to `rho_new` first (k_mdbc_gather), then are
 // applied (k_mdbc_apply) so that no thread reads a density another thread has just corrected.
 // ---------------------------------------------------------------------------------------------
+// The ghost node's sums and the solve (NeighborLoopMDBC! + the branches of ApplyMDBCCorrection, :598-622).
+// Returns 0: no new density; 1: ρ_new = sol[0] + Σ sol[k+1]·(x_i − x_ghost)[k] — the low-order branch
+// (|det A| < 1e-3, A₀₀ > 0) comes back as sol = {b₀/A₀₀, 0, …}, which that expression reproduces exactly.
+template <class T, int D>
+__device__ __forceinline__ int mdbc_node_solve(const typename Lay<T, D>::TA *__restrict__ A, const uint8_t *__restrict__ type,
+                                               const int *__restrict__ cell_start, const GridInfo *grid, const AxisMap &am,
+                                               const Phys<T> &ph, const int (&gc)[3], const T (&gp)[D], double (&sol)[D + 1]) {
+    using L = Lay<T, D>;
+    constexpr int E = D + 1;
+    const int nx = grid->nx, nm = grid->nm, ns = grid->ns;
+    int cx = gc[am.ax_f] - grid->cmin[am.ax_f];
+    int cm = (D == 3) ? gc[am.ax_m] - grid->cmin[am.ax_m] : 0;
+    int cs = gc[am.ax_s] - grid->cmin[am.ax_s];
+    double bv[E], Am[E][E];
+    for (int r = 0; r < E; ++r) {
+        bv[r] = 0.0;
+        for (int c = 0; c < E; ++c) Am[r][c] = 0.0;
+    }
+    for (int ds = -1; ds <= 1; ++ds)
+        for (int dm = (D == 3 ? -1 : 0); dm <= (D == 3 ? 1 : 0); ++dm) {
+            int rs_ = cs + ds, rm = cm + dm;
+            if (rs_ < 0 || rs_ >= ns || rm < 0 || rm >= nm) continue;
+            int x0 = max(cx - 1, 0), x1 = min(cx + 1, nx - 1);
+            if (x0 > x1) continue;
+            int rk = (rs_ * nm + rm) * nx;
+            int jb = cell_start[rk + x0], je = cell_start[rk + x1 + 1];
+            for (int j = jb; j < je; ++j) {
+                if (type[j] != 1) continue;
+                typename L::TA aj = A[j];
+                T xj[D];
+                L::pos(aj, xj);
+                T xij[D], r2 = T(0);
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    xij[k] = gp[k] - xj[k];
+                    r2 += xij[k] * xij[k];
+                }
+                if (!(r2 <= ph.H2)) continue;
+                T d = sph_sqrt(sph_abs(r2));
+                T q = sph_min(sph_max(d * ph.h_inv, T(0)), T(2));
+                T W = kernel_w(ph, q);
+                T gW[D];
+                if (ph.kernel == K_WENDLAND) {
+                    T qm2 = q - T(2);
+                    T fac = ph.gradw_c * (qm2 * qm2 * qm2);
+#pragma unroll
+                    for (int k = 0; k < D; ++k) gW[k] = fac * xij[k];
+                } else {
+                    T dwdq = (q <= T(1)) ? ph.alphaD * (T(-3) * q + T(2.25) * (q * q))
+                                         : ph.alphaD * T(-0.75) * ((T(2) - q) * (T(2) - q));
+                    T sc = dwdq * ph.h_inv;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) gW[k] = sc * xij[k] / (d + ph.eta2);
+                }
+                T Vj = ph.m0 / sph_abs(L::rhos(aj));
+                double col[E];
+                col[0] = (double)(Vj * W);
+                bv[0] += (double)(ph.m0 * W);
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    col[k + 1] = (double)(Vj * gW[k]);
+                    bv[k + 1] += (double)(ph.m0 * gW[k]);
+                }
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    Am[r][0] += col[r];
+#pragma unroll
+                    for (int c = 1; c < E; ++c) Am[r][c] += (double)(-xij[c - 1]) * col[r];
+                }
+            }
+        }
+    double detA = det_lu<E>(Am);
+    if (fabs(detA) >= 1e-3) {
+        solve_lu<E>(Am, bv, sol);
+        return 1;
+    }
+    if (Am[0][0] > 0.0) {
+        sol[0] = bv[0] / Am[0][0];
+#pragma unroll
+        for (int k = 0; k < D; ++k) sol[k + 1] = 0.0;
+        return 1;
+    }
+    return 0;
+}
+
+// ρ_new from the solve, in the reference's expression order; NaN -> ρ₀ (the `isnan` guards of :614-620)
+template <class T, int D>
+__device__ __forceinline__ T mdbc_extrapolate(const double *sol, const T (&xi)[D], const T (&gp)[D], T rho0) {
+    double v1 = sol[0];
+#pragma unroll
+    for (int k = 0; k < D; ++k) v1 = fma(sol[k + 1], (double)xi[k] - (double)gp[k], v1);
+    return (v1 == v1) ? (T)v1 : rho0;
+}
+
 template <class T, int D>
 __global__ void k_mdbc_gather(const typename Lay<T, D>::TA *__restrict__ A, const typename Lay<T, D>::TV *__restrict__ ghost,
                               const uint8_t *__restrict__ type, const int *__restrict__ cell_start, const GridInfo *grid,
@@ -271,7 +365,6 @@ __global__ void k_mdbc_gather(const typename Lay<T, D>::TA *__restrict__ A, cons
     using L = Lay<T, D>;
     constexpr int E = D + 1;
     if (ctl->error || ctl->done) return;
-    const int nx = grid->nx, nm = grid->nm, ns = grid->ns;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         has_new[i] = 0;
         T gp[D];
@@ -284,83 +377,83 @@ __global__ void k_mdbc_gather(const typename Lay<T, D>::TA *__restrict__ A, cons
         int gc[3] = {0, 0, 0};
 #pragma unroll
         for (int k = 0; k < D; ++k) gc[k] = map_floor_dev((double)gp[k], inv_cutoff, bad);
-        int cx = gc[am.ax_f] - grid->cmin[am.ax_f];
-        int cm = (D == 3) ? gc[am.ax_m] - grid->cmin[am.ax_m] : 0;
-        int cs = gc[am.ax_s] - grid->cmin[am.ax_s];
-        double bv[E], Am[E][E];
-        for (int r = 0; r < E; ++r) {
-            bv[r] = 0.0;
-            for (int c = 0; c < E; ++c) Am[r][c] = 0.0;
-        }
-        for (int ds = -1; ds <= 1; ++ds)
-            for (int dm = (D == 3 ? -1 : 0); dm <= (D == 3 ? 1 : 0); ++dm) {
-                int rs_ = cs + ds, rm = cm + dm;
-                if (rs_ < 0 || rs_ >= ns || rm < 0 || rm >= nm) continue;
-                int x0 = max(cx - 1, 0), x1 = min(cx + 1, nx - 1);
-                if (x0 > x1) continue;
-                int rk = (rs_ * nm + rm) * nx;
-                int jb = cell_start[rk + x0], je = cell_start[rk + x1 + 1];
-                for (int j = jb; j < je; ++j) {
-                    if (type[j] != 1) continue;
-                    typename L::TA aj = A[j];
-                    T xj[D];
-                    L::pos(aj, xj);
-                    T xij[D], r2 = T(0);
-#pragma unroll
-                    for (int k = 0; k < D; ++k) {
-                        xij[k] = gp[k] - xj[k];
-                        r2 += xij[k] * xij[k];
-                    }
-                    if (!(r2 <= ph.H2)) continue;
-                    T d = sph_sqrt(sph_abs(r2));
-                    T q = sph_min(sph_max(d * ph.h_inv, T(0)), T(2));
-                    T W = kernel_w(ph, q);
-                    T gW[D];
-                    if (ph.kernel == K_WENDLAND) {
-                        T qm2 = q - T(2);
-                        T fac = ph.gradw_c * (qm2 * qm2 * qm2);
-#pragma unroll
-                        for (int k = 0; k < D; ++k) gW[k] = fac * xij[k];
-                    } else {
-                        T dwdq = (q <= T(1)) ? ph.alphaD * (T(-3) * q + T(2.25) * (q * q))
-                                             : ph.alphaD * T(-0.75) * ((T(2) - q) * (T(2) - q));
-                        T sc = dwdq * ph.h_inv;
-#pragma unroll
-                        for (int k = 0; k < D; ++k) gW[k] = sc * xij[k] / (d + ph.eta2);
-                    }
-                    T Vj = ph.m0 / sph_abs(L::rhos(aj));
-                    double col[E];
-                    col[0] = (double)(Vj * W);
-                    bv[0] += (double)(ph.m0 * W);
-#pragma unroll
-                    for (int k = 0; k < D; ++k) {
-                        col[k + 1] = (double)(Vj * gW[k]);
-                        bv[k + 1] += (double)(ph.m0 * gW[k]);
-                    }
-#pragma unroll
-                    for (int r = 0; r < E; ++r) {
-                        Am[r][0] += col[r];
-#pragma unroll
-                        for (int c = 1; c < E; ++c) Am[r][c] += (double)(-xij[c - 1]) * col[r];
-                    }
-                }
-            }
-        double detA = det_lu<E>(Am);
+        double sol[E];
+        if (!mdbc_node_solve<T, D>(A, type, cell_start, grid, am, ph, gc, gp, sol)) continue;
         T xi[D];
         L::pos(A[i], xi);
-        if (fabs(detA) >= 1e-3) {
-            double sol[E];
-            solve_lu<E>(Am, bv, sol);
-            double v1 = sol[0];
+        rho_new[i] = mdbc_extrapolate<T, D>(sol, xi, gp, ph.rho0);
+        has_new[i] = 1;
+    }
+}
+
+// ---- slab mode ---------------------------------------------------------------------------------
+// A ghost node lies up to a few cells from its boundary particle, possibly across a slab face and
+// beyond the one-layer halo, so the particle's rank cannot always evaluate it.  Ghost nodes are
+// static (the reference never moves GhostPoints, Q10): every rank holds the global node table
+// (point, particle ID; ascending ID) and evaluates the nodes whose CELL lies in its owned layers —
+// the node's whole 3^D stencil is then local (owned + halo), traversed in the same order as on one
+// GPU.  out[g] = {1, sol[0..D]} or zeros; an all-reduce (sum: exactly one rank writes a node) gives
+// every rank every node's solve, and each rank extrapolates to the particles it holds (owned AND
+// halo copies, which keeps the copies identical to their originals) by looking their ID up.
+template <class T, int D>
+__global__ void k_mdbc_nodes(const typename Lay<T, D>::TA *__restrict__ A, const typename Lay<T, D>::TV *__restrict__ g_point,
+                             int ng, const uint8_t *__restrict__ type, const int *__restrict__ cell_start, const GridInfo *grid,
+                             AxisMap am, Phys<T> ph, double inv_cutoff, int own_lo, int own_hi, double *__restrict__ out,
+                             const Ctl *ctl) {
+    using L = Lay<T, D>;
+    constexpr int E = D + 1;
+    if (ctl->error || ctl->done) return;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += gridDim.x * blockDim.x) {
+        double *o = out + (size_t)g * (E + 1);
 #pragma unroll
-            for (int k = 0; k < D; ++k) v1 += sol[k + 1] * ((double)xi[k] - (double)gp[k]);
-            rho_new[i] = (v1 == v1) ? (T)v1 : ph.rho0;
-            has_new[i] = 1;
-        } else if (Am[0][0] > 0.0) {
-            double v = bv[0] / Am[0][0];
-            rho_new[i] = (v == v) ? (T)v : ph.rho0;
-            has_new[i] = 1;
+        for (int k = 0; k <= E; ++k) o[k] = 0.0;
+        T gp[D];
+        L::getv(g_point[g], gp);
+        int bad = 0;
+        int gc[3] = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < D; ++k) gc[k] = map_floor_dev((double)gp[k], inv_cutoff, bad);
+        if (gc[am.ax_s] < own_lo || gc[am.ax_s] >= own_hi) continue;   // another rank's node
+        double sol[E];
+        if (!mdbc_node_solve<T, D>(A, type, cell_start, grid, am, ph, gc, gp, sol)) continue;
+        o[0] = 1.0;
+#pragma unroll
+        for (int k = 0; k < E; ++k) o[k + 1] = sol[k];
+    }
+}
+
+template <class T, int D>
+__global__ void k_mdbc_apply_nodes(typename Lay<T, D>::TA *A, T *RN, const uint8_t *__restrict__ type,
+                                   const long long *__restrict__ id, int n, const typename Lay<T, D>::TV *__restrict__ g_point,
+                                   const long long *__restrict__ g_id, int ng, const double *__restrict__ sols, T rho0, Ctl *ctl) {
+    using L = Lay<T, D>;
+    constexpr int E = D + 1;
+    if (ctl->error || ctl->done || ng < 1) return;
+    const long long id_lo = g_id[0], id_hi = g_id[ng - 1];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const long long pid = id[i];
+        if (pid < id_lo || pid > id_hi) continue;
+        int lo = 0, hi = ng - 1;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (g_id[mid] < pid) lo = mid + 1;
+            else hi = mid;
         }
+        if (g_id[lo] != pid) continue;
+        const double *o = sols + (size_t)lo * (E + 1);
+        if (o[0] == 0.0) continue;
+        typename L::TA a = A[i];
+        T xi[D], gp[D];
+        L::pos(a, xi);
+        L::getv(g_point[lo], gp);
+        T r = mdbc_extrapolate<T, D>(o + 1, xi, gp, rho0);
+        if (!(r > T(0))) {   // see k_mdbc_apply
+            atomicCAS(&ctl->error, 0, SPH_ERR_ENUMERIC);
+            continue;
+        }
+        L::set_rhos(a, type[i] == 1 ? r : -r);
+        A[i] = a;
+        RN[i] = r;
     }
 }
 

@@ -61,6 +61,7 @@ struct sphb200_sim {
     virtual int get_stat(const char *name, double *value) = 0;
     virtual int comm_init(const uint8_t *id, int rank, int world, int axis) = 0;
     virtual int set_slab(int64_t lo, int64_t hi) = 0;
+    virtual int set_ghost_nodes(int64_t ng, const void *points, const int64_t *ids) = 0;
     virtual int column_histogram(int axis, int64_t *cell_min, int64_t *n_columns, int64_t *counts, int64_t cap) = 0;
     virtual int stage_times(double *ms_out, int n) = 0;
 };
@@ -264,6 +265,11 @@ class Sim final : public sphb200_sim {
     DevBuf<long long> id, id2;
     DevBuf<unsigned long long> group, group2, okey, okey2;
     DevBuf<uint8_t> type, type2, has_new;
+    // slab-mode mDBC: the global ghost-node table (static) and the per-node solves that are all-reduced
+    DevBuf<TV> g_point;
+    DevBuf<long long> g_id;
+    DevBuf<double> g_sol;
+    int n_ghost_nodes = -1;   // -1: no table handed over yet
     DevBuf<int> ckey, ckey2, ccoord, key_tmp, slot_tmp, tmp_idx, perm;
     // cell structure
     DevBuf<int> cell_count, cell_start, scan_partial;
@@ -556,7 +562,7 @@ class Sim final : public sphb200_sim {
         k_pack_upload<T, D><<<grid_for(count), 256, 0, stream>>>((int)count, d_pos, vel ? d_vel : nullptr,
                                                                 accel ? d_acc : nullptr, d_rho,
                                                                 (gp && prm.mdbc) ? d_gp : nullptr, type.p, ph, A.p, B.p,
-                                                                acc.p, prm.mdbc ? ghost.p : nullptr,
+                                                                acc.p, (prm.mdbc && !slab.active) ? ghost.p : nullptr,
                                                                 slab.active ? id.p : nullptr, okey.p);
         ++launches;
         CK(cudaGetLastError());
@@ -750,7 +756,7 @@ class Sim final : public sphb200_sim {
         t.A = scratch ? A2.p : A.p;
         t.B = scratch ? B2.p : B.p;
         t.acc = scratch ? acc2.p : acc.p;
-        t.ghost = prm.mdbc ? (scratch ? ghost2.p : ghost.p) : nullptr;
+        t.ghost = (prm.mdbc && !slab.active) ? (scratch ? ghost2.p : ghost.p) : nullptr;   // slab mode: node table instead (set_ghost_nodes)
         t.id = scratch ? id2.p : id.p;
         t.group = scratch ? group2.p : group.p;
         t.okey = scratch ? okey2.p : okey.p;
@@ -1018,6 +1024,7 @@ class Sim final : public sphb200_sim {
         return SPHB200_OK;
     }
     int enqueue_mdbc() {
+        if (slab.active) return slab_enqueue_mdbc();
         const int nn = (int)n;
         k_mdbc_gather<T, D><<<grid_for(nn, 128), 128, 0, stream>>>(A.p, ghost.p, type.p, cell_start.p, d_grid.p, am, nn, ph,
                                                                    prm.H_inv, rho_new.p, has_new.p, d_ctl.p);
@@ -1277,6 +1284,7 @@ class Sim final : public sphb200_sim {
     int slab_exchange_halo(TA *a, TB *b, cudaStream_t st);
     int slab_pass(int pass, TA *xa, TB *xb, cudaEvent_t *xev = nullptr);
     int slab_allreduce_ctl();
+    int slab_enqueue_mdbc();
     int slab_sort(const SlabFilter &flt, int count_rebuild);
     int slab_rebuild();
     int slab_step_body(cudaEvent_t *ev, bool host_synced = true, cudaEvent_t *xev = nullptr);
@@ -1585,6 +1593,7 @@ class Sim final : public sphb200_sim {
     // ------------------------------------------------------------------ slabs (sph_slab.cuh)
     int comm_init(const uint8_t *uid, int rank, int world, int axis) override;
     int set_slab(int64_t lo, int64_t hi) override;
+    int set_ghost_nodes(int64_t ng, const void *points, const int64_t *ids) override;
     int column_histogram(int axis, int64_t *cell_min, int64_t *n_columns, int64_t *counts, int64_t cap) override;
 #undef CK
 };
@@ -1689,6 +1698,7 @@ int sphb200_stage_times(sphb200_sim *s, double *ms, int n) { NEED(s); return s->
 int sphb200_comm_unique_id(uint8_t id_out[128]) { return slab_unique_id(id_out); }
 int sphb200_comm_init(sphb200_sim *s, const uint8_t id[128], int rank, int world, int axis) { NEED(s); return s->comm_init(id, rank, world, axis); }
 int sphb200_set_slab(sphb200_sim *s, int64_t lo, int64_t hi) { NEED(s); return s->set_slab(lo, hi); }
+int sphb200_set_ghost_nodes(sphb200_sim *s, int64_t ng, const void *points, const int64_t *ids) { NEED(s); return s->set_ghost_nodes(ng, points, ids); }
 int sphb200_column_histogram(sphb200_sim *s, int axis, int64_t *cmin, int64_t *ncol, int64_t *counts, int64_t cap) {
     NEED(s);
     return s->column_histogram(axis, cmin, ncol, counts, cap);

@@ -101,6 +101,7 @@ def lib():
         "sphb200_comm_unique_id": (C.c_int, [vp]),
         "sphb200_comm_init": (C.c_int, [sim, vp, C.c_int, C.c_int, C.c_int]),
         "sphb200_set_slab": (C.c_int, [sim, i64, i64]),
+        "sphb200_set_ghost_nodes": (C.c_int, [sim, i64, vp, P(i64)]),
         "sphb200_column_histogram": (C.c_int, [sim, C.c_int, P(i64), P(i64), vp, i64]),
     }
     for name, (res, args) in sig.items():

@@ -231,6 +231,14 @@ class Simulation:
     def set_slab(self, lo: int, hi: int):
         self._ck(self._L.sphb200_set_slab(self._h, int(lo), int(hi)))
 
+    def set_ghost_nodes(self, ghost_points: np.ndarray, particle_ids: np.ndarray):
+        """Slab-mode SimpleMDBC: the GLOBAL ghost-node table (same on every rank) — the nonzero rows of
+        SimParticles.GhostPoints and the IDs of their particles, ascending (src/SPHCellList.jl:228-231)."""
+        gp = np.ascontiguousarray(ghost_points, dtype=self.dtype).reshape(-1, self.D)
+        ids = np.ascontiguousarray(particle_ids, dtype=np.int64)
+        assert gp.shape[0] == ids.shape[0]
+        self._ck(self._L.sphb200_set_ghost_nodes(self._h, int(ids.shape[0]), _ptr(gp), ids.ctypes.data_as(C.POINTER(C.c_int64))))
+
 
 def comm_unique_id() -> bytes:
     buf = (C.c_uint8 * 128)()

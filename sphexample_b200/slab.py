@@ -128,8 +128,19 @@ class SlabDecomposition:
         self.sim.set_slab(lo, hi)
         return self
 
+    def ghost_node_table(self):
+        """(points, particle IDs) of the particles that have a ghost node (nonzero GhostPoints row, Q10),
+        ascending ID — the whole table, identical on every rank."""
+        gp = np.asarray(self.parts.GhostPoints)
+        has = np.any(gp != 0, axis=1)
+        ids = np.asarray(self.parts.ID, np.int64)[has]
+        o = np.argsort(ids, kind="stable")
+        return gp[has][o], ids[o]
+
     def setup(self):
         self.join()
+        if getattr(self.sim.params, "mdbc", 0):
+            self.sim.set_ghost_nodes(*self.ghost_node_table())
         self.sim.upload(self.parts.permuted(self.mine))
         return self
 

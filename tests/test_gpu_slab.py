@@ -65,6 +65,53 @@ def test_every_slab_axis_reproduces_the_reference_roles(oracle_lib, name, axis):
         util.check(util.relerr(b[k], util.by_id(o.ids, o.get(of))), tol)
 
 
+@pytest.mark.parametrize("axis", [1, 0])
+def test_mdbc_in_slab_mode_world_of_one(oracle_lib, axis):
+    """SimpleMDBC through the slab-mode path (global ghost-node table, solves all-reduced, extrapolation by
+    particle ID) against the per-particle single-GPU path and the oracle (C5, moving state)"""
+    case = util.perturb(util.case_c5("float64"))
+    p = util.params_of(case)
+    assert p.mdbc == 1
+    ref = Simulation(p)
+    ref.upload(case.particles)
+    r0 = ref.step(60, reset_delta_x=True)
+    a = ref.download(order="id")
+    ref.close()
+    sim = Simulation(p)
+    dec = slab.SlabDecomposition(sim, case.particles, p.H_inv, 0, 1, axis=axis).setup()
+    gp, gid = dec.ghost_node_table()
+    assert gp.shape[0] > 500 and np.all(np.diff(gid) > 0)
+    r1 = sim.step(60, reset_delta_x=True)
+    b = dec.gather(order="id", fields=("Position", "Velocity", "Density", "Pressure", "ID"))
+    sim.close()
+    o = oracle_lib.Oracle(p, case.particles, nthreads=4)
+    o.step(60, True)
+    assert r0["n_rebuilds"] == r1["n_rebuilds"] == o.report()["n_rebuilds"]
+    bnd = np.asarray(case.particles.Type)[np.argsort(case.particles.ID, kind="stable")] != 1
+    assert np.any(np.abs(b["Density"][bnd] - 1000.0) > 1e-3)       # the correction did something
+    for k, of, tol in (("Position", "pos", 1e-13), ("Velocity", "vel", 1e-8), ("Density", "rho", 1e-11)):
+        if axis == 1:   # same cell order as the plain run: same traversal, same sums
+            assert np.array_equal(a[k], b[k]), k
+        util.check(util.relerr(b[k], a[k]), tol)
+        util.check(util.relerr(b[k], util.by_id(o.ids, o.get(of))), tol * 10)
+
+
+def test_mdbc_in_slab_mode_needs_the_node_table():
+    from sphexample_b200.simulation import SphError
+    case = util.case_c5("float64")
+    p = util.params_of(case)
+    sim = Simulation(p)
+    with pytest.raises(SphError):
+        sim.set_ghost_nodes(np.zeros((1, 2)), np.ones(1, np.int64))    # before comm_init
+    dec = slab.SlabDecomposition(sim, case.particles, p.H_inv, 0, 1, axis=1).join()
+    with pytest.raises(SphError):
+        sim.set_ghost_nodes(np.zeros((2, 2)), np.array([5, 5], np.int64))   # IDs not strictly ascending
+    sim.upload(case.particles)
+    with pytest.raises(SphError):
+        sim.step(1, reset_delta_x=True)                                 # no table: refuse, do not skip S6
+    sim.close()
+
+
 def test_slab_mode_rejects_unsupported_setups():
     from sphexample_b200.simulation import SphError, comm_unique_id
     case = util.case_3d_small("float32")
