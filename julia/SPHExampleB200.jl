@@ -181,4 +181,39 @@ function SimulationLoop!(h::Handle, SimMetaData, SimParticles, t_next::Real; dow
     return rep
 end
 
+# ---- several GPUs (one process per GPU; see INTEGRATION.md) --------------------------------------
+"""
+    comm_unique_id() -> Vector{UInt8}            (rank 0; broadcast the 128 bytes to the other ranks)
+    comm_init!(h, id, rank, world, axis)         (axis 0 = x, 1 = y, 2 = z), then set_slab!(h, lo, hi), then upload!
+"""
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    rc = ccall((:sphb200_comm_unique_id, libsphb200), Cint, (Ptr{UInt8},), id)
+    rc == 0 || error("sphb200_comm_unique_id failed ($rc): is libnccl loadable?")
+    return id
+end
+comm_init!(h::Handle, id::Vector{UInt8}, rank::Integer, world::Integer, axis::Integer) =
+    check(h.ptr, ccall((:sphb200_comm_init, libsphb200), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint, Cint), h.ptr, id, rank, world, axis))
+set_slab!(h::Handle, lo::Integer, hi::Integer) =
+    check(h.ptr, ccall((:sphb200_set_slab, libsphb200), Cint, (Ptr{Cvoid}, Int64, Int64), h.ptr, lo, hi))
+
+"""
+    set_ghost_nodes!(h, SimParticles)
+
+SimpleMDBC in slab mode: every rank passes the WHOLE table's nonzero `GhostPoints` rows with the IDs of
+their particles, ascending by ID (call with the full, ID-sorted SimParticles, before `upload!` of the
+rank's share).
+"""
+function set_ghost_nodes!(h::Handle, SimParticles)
+    sel = findall(!iszero, SimParticles.GhostPoints)
+    sel = sel[sortperm(SimParticles.ID[sel])]
+    pts = SimParticles.GhostPoints[sel]
+    ids = Vector{Int64}(SimParticles.ID[sel])
+    GC.@preserve pts ids begin
+        rc = ccall((:sphb200_set_ghost_nodes, libsphb200), Cint, (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Int64}),
+                   h.ptr, length(ids), pointer(pts), pointer(ids))
+    end
+    check(h.ptr, rc)
+end
+
 end # module

@@ -226,6 +226,8 @@ class SimulationMetaData:
     SimulationTime: float = 0.0
     IndexCounter: int = 0
     TimeSteps: list = field(default_factory=list)
+    ExportSingleVTKHDF: bool = True       # :49 one transient .vtkhdf file (True) or one file per output (False)
+    OutputVariables: Optional[Sequence[str]] = None    # :51-65; None = the reference's default list
 
     def __post_init__(self):
         if self.OutputTimes is None:

@@ -1,8 +1,12 @@
-"""Particle dump in the layout of the reference's input CSVs (the step after the
-hot path).  The reference writes VTKHDF (src/ProduceHDFVTK.jl), which needs libhdf5 — absent in
-this image; a dump in the DualSPHysics column layout the loader already reads
-(`Idp, Vel:0..2, Rhop, Press, Type, Mk, Points:0..2`, src/PreProcess.jl:12-43) is the parity
-artefact instead: the state can be diffed against a reference run or fed back as an input case."""
+"""Output writers (the step after the hot path).
+
+* `write_particles_csv`: particle dump in the DualSPHysics column layout the loader already reads
+  (`Idp, Vel:0..2, Rhop, Press, Type, Mk, Points:0..2`, src/PreProcess.jl:12-43) — the parity artefact:
+  the state can be diffed against a reference run or fed back as an input case.
+* `SaveVTKHDF`, `VTKHDFTransient`, `SetupVTKOutput`: the reference's VTKHDF PolyData files
+  (src/ProduceHDFVTK.jl:120-325,461-621), one file per output or one transient file, written through
+  the hand-rolled HDF5 writer `hdf5_min` (no libhdf5 / h5py in this image).
+* `write_particles_vtp`: the same point data as VTK XML PolyData."""
 from __future__ import annotations
 
 import csv
@@ -90,3 +94,206 @@ def write_particles_vtp(path: str, state: dict, select=None) -> int:
             fh.write(b)
         fh.write(b"\n</AppendedData>\n</VTKFile>\n")
     return n
+
+
+# ---------------------------------------------------------------------------------------------------
+# VTKHDF (src/ProduceHDFVTK.jl).  Dataset shapes are HDF5 (row-major) shapes: the reference's Julia
+# arrays are column-major, so its 3×N `Points` is the N×3 dataset written here.
+# ---------------------------------------------------------------------------------------------------
+OUTPUT_VARIABLES = ["ChunkID", "Kernel", "KernelGradient", "Density", "Pressure", "Velocity", "Acceleration", "BoundaryBool",
+                    "ID", "Type", "GroupMarker", "GhostPoints", "GhostNormals"]     # SimMetaData.OutputVariables default, :50-64
+
+
+def to_3d(a: np.ndarray) -> np.ndarray:
+    """`to_3d!` (src/AuxiliaryFunctions.jl:28-34): 2D vectors get a zero third component, same element type
+    (note: (v1, v2, 0) — not the (x, 0, z) column convention of the input CSVs)."""
+    a = np.asarray(a)
+    if a.ndim == 1 or a.shape[1] == 3:
+        return a
+    out = np.zeros((a.shape[0], 3), a.dtype)
+    out[:, :a.shape[1]] = a
+    return out
+
+
+def _empty_connectivity(g, name, n_cells_entries):
+    c = g.group(name)
+    for ds, val in (("NumberOfCells", n_cells_entries), ("NumberOfConnectivityIds", n_cells_entries),
+                    ("Connectivity", np.zeros(0, np.int64)), ("Offsets", np.zeros(1, np.int64))):
+        c.dataset(ds, np.asarray(val, np.int64))
+
+
+def SaveVTKHDF(filepath: str, points: np.ndarray, variable_names=(), *args) -> int:
+    """`SaveVTKHDF` (src/ProduceHDFVTK.jl:120-160): one static PolyData file — /VTKHDF with Version [2, 3]
+    and the ASCII Type attribute, NumberOfPoints, Points, PointData/<name>, Vertices (one vertex cell per
+    point) and empty Lines / Polygons / Strips groups.  Returns the file size."""
+    from . import hdf5_min as h5
+    assert len(variable_names) == len(args), "Same number of variable_names as args is necessary"
+    points = to_3d(points)
+    n = int(points.shape[0])
+    root = h5.Group()
+    g = root.group("VTKHDF")
+    g.attrs["Version"] = np.array([2, 3], np.int64)
+    g.attrs["Type"] = b"PolyData"
+    g.dataset("NumberOfPoints", np.array([n], np.int64))
+    g.dataset("Points", points)
+    pd = g.group("PointData")
+    for name, a in zip(variable_names, args):
+        pd.dataset(name, to_3d(a))
+    v = g.group("Vertices")
+    v.dataset("NumberOfCells", np.array([n], np.int64))
+    v.dataset("NumberOfConnectivityIds", np.array([n], np.int64))
+    v.dataset("Connectivity", np.arange(n, dtype=np.int64))
+    v.dataset("Offsets", np.arange(n + 1, dtype=np.int64))
+    for name in ("Lines", "Polygons", "Strips"):
+        _empty_connectivity(g, name, np.zeros(1, np.int64))
+    return h5.write_file(filepath, root)
+
+
+class VTKHDFTransient:
+    """The single-file mode (`GenerateGeometryStructure` + `GenerateStepStructure` + `AppendVTKHDFData`,
+    src/ProduceHDFVTK.jl:163-325): every `append` adds one step to /VTKHDF/Steps and to the growing
+    NumberOfPoints / Points / PointData datasets.  The reference keeps the HDF5 file open and extends
+    chunked datasets; here the rows are spooled and the file — same groups, datasets, shapes, types and
+    values, contiguous instead of chunked storage — is laid out by `close()`.
+
+    Reference behaviour kept as it is: Points are Float64 (`fType`), Version is Int32, the four
+    connectivity groups get one zero per step in each dataset (no vertex cells in this mode), and
+    Steps/NumberOfParts grows by TWO entries per step (:283-285 and :296-298)."""
+
+    def __init__(self, filepath: str, variable_names, *init_args, vertices: bool = False):
+        from . import hdf5_min as h5
+        assert len(variable_names) == len(init_args), "Same number of variable_names as args is necessary"
+        self._h5, self.filepath, self.names, self.vertices = h5, filepath, list(variable_names), bool(vertices)
+        self.points = h5.Spool(np.float64, (3,))
+        self.vars = []
+        for a in init_args:
+            a = np.asarray(a)
+            self.vars.append(h5.Spool(a.dtype, (3,) if a.ndim == 2 else ()))
+        self.values, self.npoints = [], []
+        self.conn = h5.Spool(np.int64) if vertices else None
+        self.offs = h5.Spool(np.int64) if vertices else None
+        self.closed = False
+
+    def append(self, new_step: float, positions: np.ndarray, *args):
+        """`AppendVTKHDFData(root, newStep, Positions, variable_names, args...)`"""
+        assert len(args) == len(self.vars) and not self.closed
+        pos = to_3d(positions)
+        n = int(pos.shape[0])
+        self.points.append(pos)
+        for sp, a in zip(self.vars, args):
+            a = to_3d(a)
+            assert a.shape[0] == n
+            sp.append(a)
+        self.values.append(float(new_step))
+        self.npoints.append(n)
+        if self.vertices:
+            self.conn.append(np.arange(n, dtype=np.int64))
+            self.offs.append(np.arange(n + 1, dtype=np.int64))
+
+    def close(self) -> int:
+        if self.closed:
+            return 0
+        h5 = self._h5
+        ns = len(self.values)
+        npts = np.asarray(self.npoints, np.int64)
+        poff = np.concatenate([[0], np.cumsum(npts)[:-1]]).astype(np.int64) if ns else np.zeros(0, np.int64)
+        root = h5.Group()
+        g = root.group("VTKHDF")
+        g.attrs["Version"] = np.array([2, 3], np.int32)
+        g.attrs["Type"] = b"PolyData"
+        g.dataset("NumberOfPoints", npts)
+        g.dataset("Points", self.points)
+        pd = g.group("PointData")
+        for name, sp in zip(self.names, self.vars):
+            pd.dataset(name, sp)
+        zeros = np.zeros(ns, np.int64)
+        cell_off = np.zeros((ns, 4), np.int64)
+        conn_off = np.zeros((ns, 4), np.int64)
+        for name in ("Vertices", "Lines", "Polygons", "Strips"):
+            c = g.group(name)
+            if name == "Vertices" and self.vertices:      # option: real vertex cells, so that ParaView renders the points
+                c.dataset("NumberOfCells", npts)
+                c.dataset("NumberOfConnectivityIds", npts)
+                c.dataset("Connectivity", self.conn)
+                c.dataset("Offsets", self.offs)
+                cell_off[:, 0] = poff
+                conn_off[:, 0] = poff
+            else:
+                for ds in ("NumberOfConnectivityIds", "NumberOfCells", "Offsets", "Connectivity"):
+                    c.dataset(ds, zeros)
+        st = g.group("Steps")
+        st.attrs["NSteps"] = np.int32(ns)
+        st.dataset("Values", np.asarray(self.values, np.float64))
+        st.dataset("PartOffsets", np.arange(ns, dtype=np.int64))
+        st.dataset("NumberOfParts", np.ones(2 * ns, np.int64))
+        st.dataset("PointOffsets", poff)
+        st.dataset("CellOffsets", cell_off)
+        st.dataset("ConnectivityIdOffsets", conn_off)
+        pdo = st.group("PointDataOffsets")
+        for name in self.names:
+            pdo.dataset(name, poff)
+        size = h5.write_file(self.filepath, root)
+        for sp in [self.points, *self.vars] + ([self.conn, self.offs] if self.vertices else []):
+            sp.close()
+        self.closed = True
+        return size
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def vtk_point_data(state: dict, particles=None, variable_names=None):
+    """The `available` dictionary of `save_particle_data` (src/ProduceHDFVTK.jl:563-577) from a
+    `Simulation.download()` state (+ the host `SimParticles` table for the columns that never change on
+    the device: GhostPoints, GhostNormals, BoundaryBool — matched by ID).  Returns (names, arrays) for
+    the requested variables that are available."""
+    n = int(np.asarray(state["Position"]).shape[0])
+    T = np.asarray(state["Position"]).dtype
+    D = int(np.asarray(state["Position"]).shape[1])
+    avail = {}
+    for k in ("Density", "Pressure", "Velocity", "Acceleration", "ID", "GroupMarker", "Kernel", "KernelGradient"):
+        if k in state:
+            avail[k] = np.asarray(state[k])
+    if "Type" in state:
+        typ = np.asarray(state["Type"])
+        avail["Type"] = typ.astype(np.int8)                                    # `Int8.(SimParticles.Type)`
+        avail["BoundaryBool"] = (typ != 1).astype(np.uint8)                    # src/PreProcess.jl:78-98: 1 - MotionLimiter
+    avail.setdefault("ChunkID", np.zeros(n, np.int64))                         # threading detail of the reference's loop; 0 here
+    avail.setdefault("Kernel", np.zeros(n, T))
+    avail.setdefault("KernelGradient", np.zeros((n, D), T))
+    if particles is not None and "ID" in state:
+        order = np.argsort(np.asarray(particles.ID), kind="stable")
+        row = order[np.searchsorted(np.asarray(particles.ID)[order], np.asarray(state["ID"]))]
+        avail["GhostPoints"] = np.asarray(particles.GhostPoints, T)[row]
+        avail["GhostNormals"] = np.asarray(particles.GhostNormals, T)[row]
+    else:
+        avail.setdefault("GhostPoints", np.zeros((n, D), T))
+        avail.setdefault("GhostNormals", np.zeros((n, D), T))
+    names = [v for v in (OUTPUT_VARIABLES if variable_names is None else variable_names) if v in avail]
+    return names, [avail[v] for v in names]
+
+
+def SetupVTKOutput(save_location: str, simulation_name: str, export_single: bool = True, variable_names=None, particles=None):
+    """`SetupVTKOutput` (src/ProduceHDFVTK.jl:461-621) for particle files: returns (save_particles(iteration,
+    total_time, state), close_files()).  Multi-file mode writes `<name>_<iteration, 6 digits>.vtkhdf`, single-file
+    mode appends to `<name>.vtkhdf`."""
+    import os
+    base = os.path.join(save_location, simulation_name)
+    tr = {"w": None}
+
+    def save_particles(iteration: int, total_time: float, state: dict):
+        names, arrays = vtk_point_data(state, particles, variable_names)
+        if not export_single:
+            return SaveVTKHDF(f"{base}_{int(iteration):06d}.vtkhdf", state["Position"], names, *arrays)
+        if tr["w"] is None:
+            tr["w"] = VTKHDFTransient(base + ".vtkhdf", names, *arrays)
+        tr["w"].append(total_time, state["Position"], *arrays)
+
+    def close_files():
+        if tr["w"] is not None:
+            tr["w"].close()
+
+    return save_particles, close_files

@@ -8,6 +8,7 @@ tests read like the reference's own loop.  `RunSimulation` mirrors the driver
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Optional
 
 import numpy as np
@@ -268,6 +269,18 @@ def RunSimulation(*, SimGeometry=(), SimMetaData, SimConstants, SimKernel, SimPa
     if meta.TotalTime != 0.0 or meta.Iteration != 0:      # a restart: the device clock drives ProgressMotion and the loop condition
         sim.set_time(meta.TotalTime, meta.Iteration)
     outputs = 0
+    close_files = None
+    if save_particles is None and meta.SaveLocation:
+        # the reference's own output: VTKHDF particle files under SaveLocation (SetupVTKOutput, :845-849),
+        # the initial state first, with OutputIterationCounter = 1
+        from . import output as _out
+        os.makedirs(meta.SaveLocation, exist_ok=True)
+        save_vtk, close_files = _out.SetupVTKOutput(meta.SaveLocation, meta.SimulationName or "Simulation",
+                                                    export_single=bool(getattr(meta, "ExportSingleVTKHDF", True)),
+                                                    variable_names=getattr(meta, "OutputVariables", None), particles=SimParticles)
+        save_particles = lambda counter, state, rep: save_vtk(counter, rep["total_time"] if rep else meta.TotalTime, state)
+        meta.OutputIterationCounter = 1
+        save_particles(1, sim.download(), None)
     try:
         while True:
             rep = sim.SimulationLoop(next_output_time(meta))                          # :883
@@ -285,5 +298,7 @@ def RunSimulation(*, SimGeometry=(), SimMetaData, SimConstants, SimKernel, SimPa
                 break
         state = sim.download(order="id")
     finally:
+        if close_files is not None:
+            close_files()                                                             # "13B Close Data Streams", :911
         sim.close()
     return state

@@ -139,7 +139,7 @@ class SlabDecomposition:
 
     def setup(self):
         self.join()
-        if getattr(self.sim.params, "mdbc", 0):
+        if getattr(getattr(self.sim, "params", None), "mdbc", 0):
             self.sim.set_ghost_nodes(*self.ghost_node_table())
         self.sim.upload(self.parts.permuted(self.mine))
         return self

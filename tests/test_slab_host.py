@@ -137,3 +137,17 @@ def test_two_ranks_partition_broadcast_and_gather_with_gloo():
     case = util.case_3d_small("float32")
     assert min(n0, n1) > 0
     assert chk0 == (True, True) and chk1 is None              # rank 0 got the whole table back, by ID
+
+
+def test_ghost_node_table_is_the_nonzero_ghost_rows_by_ascending_id():
+    """slab-mode SimpleMDBC hands every rank the same static node table (sphb200_set_ghost_nodes)"""
+    case = util.case_c5("float64")
+    p = case.particles
+    shuffled = p.permuted(np.random.default_rng(3).permutation(len(p)))
+    dec = slab.SlabDecomposition(_FakeSim(), shuffled, util.params_of(case).H_inv, 0, 2, axis=0)
+    gp, gid = dec.ghost_node_table()
+    has = np.any(p.GhostPoints != 0, axis=1)
+    assert gp.shape == (int(has.sum()), 2) and gp.shape[0] > 500
+    assert np.all(np.diff(gid) > 0) and np.array_equal(gid, np.sort(p.ID[has]))
+    o = np.argsort(p.ID[has], kind="stable")
+    assert np.array_equal(gp, p.GhostPoints[has][o])
