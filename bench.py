@@ -316,8 +316,9 @@ def run_ours(args, rank, world, local_rank):
     st0 = sim.download(fields=("Position", "Velocity", "Density", "Type", "ID", "GroupMarker"))
     vmax_local = float(np.sqrt((st0["Velocity"].astype(np.float64) ** 2).sum(1)).max())
     host = {k: torch.from_numpy(np.ascontiguousarray(st0[k])).pin_memory().numpy() for k in ("Position", "Velocity", "Density")}
-    types = np.ascontiguousarray(st0["Type"], np.uint8)
-    ids = np.ascontiguousarray(st0["ID"], np.int64)
+    # (every column of the host table is pinned: a pageable column would go through the driver's staging buffer)
+    types = torch.from_numpy(np.ascontiguousarray(st0["Type"], np.uint8)).pin_memory().numpy()
+    ids = torch.from_numpy(np.ascontiguousarray(st0["ID"], np.int64)).pin_memory().numpy()
     n_local = int(types.shape[0])
 
     def upload():

@@ -54,6 +54,10 @@ struct Ctl {
     double list_build_equiv;   // builds so far in units of "all bricks once" (what sphb200_get_stat("list_builds") reports)
     double vmax_now;           // max |v| at this step head (incl. moving bodies)
     long long list_missing;    // test hook (option verify_lists): pairs within H found missing from a list in use
+    // lean step sequence (single GPU): the captured step holds no UpdateNeighbors! chain; a step that needs one
+    // pauses itself (done = 1, paused = 1) and the host runs its body with the chain
+    int paused;
+    double last_disp4;         // what the last step head added to delta_x (4 x the largest half-step displacement)
 };
 
 enum { LIST_BUILD_NONE = 0, LIST_BUILD_ALL = 1, LIST_BUILD_FLAGGED = 2 };   // Ctl::list_build
@@ -158,6 +162,7 @@ SPH_HD void step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, double list
     }
     if (ctl->done) return;
     ctl->delta_x = (double)((T)ctl->delta_x + T(4) * disp);
+    ctl->last_disp4 = (double)(T(4) * disp);
     T dt1 = sph_sqrt(h / sph_sqrt(acc2));   // +inf when every acceleration is zero (first step)
     T dt2 = h / (c0 + visc);
     T dt = cfl * sph_min(dt1, dt2);
@@ -222,7 +227,10 @@ SPH_HD void step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, double list
             }
         }
     }
-    if (pause_on_rebuild && ctl->do_rebuild) ctl->done = 1;
+    if (pause_on_rebuild && ctl->do_rebuild) {
+        ctl->done = 1;
+        ctl->paused = 1;
+    }
 }
 
 // UpdateMetaData!, src/SPHCellList.jl:679-685 (S19)

@@ -722,7 +722,13 @@ __device__ __forceinline__ void pair_fast_x2(const FastTarget<float> &a, const F
 // =================================================================================================
 // The LIST kernel (see the file header).
 // =================================================================================================
-template <class T, int D, int PASS, bool GENERIC>
+// SPLIT (1 or 4): lanes per target.  A lane normally walks the whole list of its own target; with a few
+// thousand fp64 particles that is one long chain per lane on a handful of warps (C1: 27 us per pass on 4
+// warps of 54 SMs, each warp alone on its fp64 pipe) while most of the GPU idles.  With SPLIT = 4 a
+// sub-brick is 8 targets: lane l serves target l / 4 and takes every 4th list chunk, starting at chunk
+// l % 4; the partial sums (linear: FastSums) meet in two shuffles and lane 0 of the quad runs the epilogue.
+// Same lists, same accepted pairs; only the order of the summation differs.  Host picks it by size.
+template <class T, int D, int PASS, bool GENERIC, int SPLIT = 1>
 __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interact_ring(const InteractArgs<T, D> g) {
     using L = Lay<T, D>;
     using TA = typename L::TA;
@@ -733,6 +739,8 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
     constexpr int NSLOT = RG::NSLOT, CAP = RG::CAP, NCW = RG::NCW;
     constexpr int LIST_PF = SPH_RING_LIST_PF;   // list chunks in flight per lane
     constexpr bool PACKED = !GENERIC && std::is_same<T, float>::value && SPH_RING_PACKED;   // pair_fast_x2
+    static_assert(SPLIT == 1 || (SPLIT == 4 && !GENERIC && !PACKED), "split lists: the scalar fast pair body only");
+    constexpr int TPS = 32 / SPLIT;             // targets per sub-brick
     constexpr int OFF_B = CAP * SS::esA, OFF_R = OFF_B + CAP * SS::esB, OFF_BN = OFF_R + CAP * SS::esR;
     static_assert(OFF_BN + CAP * SS::esBn <= RG::SLOT_BYTES, "ring slot too small");
 
@@ -873,7 +881,7 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
         mbar_wait(&s_full[slot], use & 1u);
         if (s_meta[slot][2] < 0) break;
         const int t0 = s_meta[slot][0], t1 = s_meta[slot][1], bidx = s_meta[slot][3];
-        const int nsub = (t1 - t0 + 31) >> 5;
+        const int nsub = (t1 - t0 + TPS - 1) / TPS;
         const unsigned char *const sb = smem_raw + (size_t)slot * RG::SLOT_BYTES;
         const TA *const sA = reinterpret_cast<const TA *>(sb);
         const TB *const sB = reinterpret_cast<const TB *>(sb + OFF_B);
@@ -894,8 +902,9 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
             if (sub >= nsub) break;
 
             // ---- this lane's target particle -------------------------------------------------
-            const int i = t0 + sub * 32 + lane;
+            const int i = t0 + sub * TPS + lane / SPLIT;
             const bool valid = i < t1;
+            [[maybe_unused]] const int sq = lane % SPLIT;   // which chunks of the target's list this lane takes
             T xa[D], va[D], rho_a = T(1), P_a = T(0), rhon_a = T(1), ml_a = T(0);
 #pragma unroll
             for (int k = 0; k < D; ++k) xa[k] = va[k] = T(0);
@@ -927,12 +936,14 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
             // shared-memory gathers (a write-after-read stall that cost 40 % of the kernel, profiles/r2c).
             const int last_chunk = (g.lcap >> 3) - 1;
             const size_t lstride = g.nl_stride;
-            const uint4 *pp[LIST_PF];
-            uint4 pf[LIST_PF];
+            [[maybe_unused]] const uint4 *pp[LIST_PF];
+            [[maybe_unused]] uint4 pf[LIST_PF];
+            if constexpr (SPLIT == 1) {
 #pragma unroll
-            for (int d = 0; d < LIST_PF; ++d) {
-                pp[d] = g.nl + (valid ? i : t0) + (size_t)min(d, last_chunk) * lstride;
-                pf[d] = ld_nc_v4(pp[d]);
+                for (int d = 0; d < LIST_PF; ++d) {
+                    pp[d] = g.nl + (valid ? i : t0) + (size_t)min(d, last_chunk) * lstride;
+                    pf[d] = ld_nc_v4(pp[d]);
+                }
             }
             PairSide<T, D> sa;
             PairAccum<T, D> sacc;
@@ -1050,15 +1061,34 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
                     }
                 }
             };
-            const int pf_last = min(last_chunk, mchunk - 1);   // nothing beyond the warp's longest list is fetched from DRAM
-            for (int c0 = 0; c0 < mchunk; c0 += LIST_PF) {
+            if constexpr (SPLIT == 1) {
+                const int pf_last = min(last_chunk, mchunk - 1);   // nothing beyond the warp's longest list is fetched from DRAM
+                for (int c0 = 0; c0 < mchunk; c0 += LIST_PF) {
 #pragma unroll
-                for (int d = 0; d < LIST_PF; ++d) {
-                    if (d == 0 || c0 + d < mchunk) {   // (warp-uniform)
-                        chunk_body(c0 + d, pf[d]);
-                        if (c0 + d + LIST_PF <= pf_last) pp[d] += (size_t)LIST_PF * lstride;   // (else: re-read, an L2 hit)
-                        pf[d] = ld_nc_v4(pp[d]);
+                    for (int d = 0; d < LIST_PF; ++d) {
+                        if (d == 0 || c0 + d < mchunk) {   // (warp-uniform)
+                            chunk_body(c0 + d, pf[d]);
+                            if (c0 + d + LIST_PF <= pf_last) pp[d] += (size_t)LIST_PF * lstride;   // (else: re-read, an L2 hit)
+                            pf[d] = ld_nc_v4(pp[d]);
+                        }
                     }
+                }
+            } else {
+                // chunks sq, sq + SPLIT, ... of the target's list; one chunk prefetched ahead
+                const uint4 *const lp = g.nl + (valid ? i : t0);
+                const int mloop = (mchunk + SPLIT - 1) / SPLIT;     // (mchunk: the warp's longest list)
+                uint4 nxt = ld_nc_v4(lp + (size_t)min(sq, last_chunk) * lstride);
+                for (int k = 0; k < mloop; ++k) {
+                    const uint4 raw = nxt;
+                    nxt = ld_nc_v4(lp + (size_t)min(sq + (k + 1) * SPLIT, last_chunk) * lstride);
+                    chunk_body(sq + k * SPLIT, raw);               // beyond the list's end: the padding chunk
+                }
+#pragma unroll
+                for (int off = 1; off < SPLIT; off <<= 1) {
+                    fs.s1 += __shfl_xor_sync(0xffffffffu, fs.s1, off);
+                    fs.s2 += __shfl_xor_sync(0xffffffffu, fs.s2, off);
+#pragma unroll
+                    for (int k = 0; k < D; ++k) fs.s3[k] += __shfl_xor_sync(0xffffffffu, fs.s3[k], off);
                 }
             }
             T drho = T(0), acc[D];
@@ -1066,7 +1096,8 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
             for (int k = 0; k < D; ++k) acc[k] = T(0);
             if constexpr (PACKED) fast_finish2<D>(ft, fs2, drho, acc);
             else if (!GENERIC) fast_finish<T, D>(ft, fs, drho, acc);
-            if (valid) interact_epilogue<T, D, PASS, GENERIC>(g, i, xa, va, rho_a, sacc, drho, acc, red, g.epilogue == EPI_FUSED ? &epf : nullptr);
+            if (valid && (SPLIT == 1 || sq == 0))
+                interact_epilogue<T, D, PASS, GENERIC>(g, i, xa, va, rho_a, sacc, drho, acc, red, g.epilogue == EPI_FUSED ? &epf : nullptr);
 
             if (bidx < nbnd) {
                 // slab mode: the warp that retires the last sub-brick of the last boundary brick

@@ -145,7 +145,7 @@ int Sim<T, D>::slab_enqueue_mdbc() {
     if (n_ghost_nodes < 0) return fail(SPHB200_ESTATE, "SimpleMDBC in slab mode needs the ghost-node table (sphb200_set_ghost_nodes) before the first step");
     const int ng = n_ghost_nodes;
     if (ng == 0) return SPHB200_OK;
-    k_mdbc_nodes<T, D><<<grid_for(ng, 128), 128, 0, stream>>>(A.p, g_point.p, ng, type.p, cell_start.p, d_grid.p, am, ph, prm.H_inv,
+    k_mdbc_nodes<T, D><<<grid_for((int64_t)ng * 32, 128), 128, 0, stream>>>(A.p, g_point.p, ng, type.p, cell_start.p, d_grid.p, am, ph, prm.H_inv,
                                                               own_lo, own_hi, g_sol.p, d_ctl.p);
     ++launches;
     CKS(cudaGetLastError());
@@ -421,6 +421,7 @@ int Sim<T, D>::slab_pass(int pass, TA *xa, TB *xb, cudaEvent_t *xev) {
 template <class T, int D>
 int Sim<T, D>::slab_resume_after_pause() {
     h_ctl->done = 0;
+    h_ctl->paused = 0;
     int rc = push_ctl();
     if (rc) return rc;
     return slab_rebuild();

@@ -266,12 +266,17 @@ __global__ void k_full_step(typename Lay<T, D>::TA *A, typename Lay<T, D>::TB *B
 // The ghost node's sums and the solve (NeighborLoopMDBC! + the branches of ApplyMDBCCorrection, :598-622).
 // Returns 0: no new density; 1: ρ_new = sol[0] + Σ sol[k+1]·(x_i − x_ghost)[k] — the low-order branch
 // (|det A| < 1e-3, A₀₀ > 0) comes back as sol = {b₀/A₀₀, 0, …}, which that expression reproduces exactly.
+// WARP-cooperative: all 32 lanes call it for the SAME node (a node has ~120 candidates, one thread per node
+// made the kernel a 65 us latency chain on C5); lane l takes candidates l, l + 32, … of every row of the
+// stencil, the partial sums are combined by a butterfly (same order on every lane: all lanes hold the
+// same sums and take the same branch).
 template <class T, int D>
 __device__ __forceinline__ int mdbc_node_solve(const typename Lay<T, D>::TA *__restrict__ A, const uint8_t *__restrict__ type,
                                                const int *__restrict__ cell_start, const GridInfo *grid, const AxisMap &am,
                                                const Phys<T> &ph, const int (&gc)[3], const T (&gp)[D], double (&sol)[D + 1]) {
     using L = Lay<T, D>;
     constexpr int E = D + 1;
+    const int lane = threadIdx.x & 31;
     const int nx = grid->nx, nm = grid->nm, ns = grid->ns;
     int cx = gc[am.ax_f] - grid->cmin[am.ax_f];
     int cm = (D == 3) ? gc[am.ax_m] - grid->cmin[am.ax_m] : 0;
@@ -289,7 +294,7 @@ __device__ __forceinline__ int mdbc_node_solve(const typename Lay<T, D>::TA *__r
             if (x0 > x1) continue;
             int rk = (rs_ * nm + rm) * nx;
             int jb = cell_start[rk + x0], je = cell_start[rk + x1 + 1];
-            for (int j = jb; j < je; ++j) {
+            for (int j = jb + lane; j < je; j += 32) {
                 if (type[j] != 1) continue;
                 typename L::TA aj = A[j];
                 T xj[D];
@@ -334,6 +339,15 @@ __device__ __forceinline__ int mdbc_node_solve(const typename Lay<T, D>::TA *__r
                 }
             }
         }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+            bv[r] += __shfl_xor_sync(0xffffffffu, bv[r], off);
+#pragma unroll
+            for (int c = 0; c < E; ++c) Am[r][c] += __shfl_xor_sync(0xffffffffu, Am[r][c], off);
+        }
+    }
     double detA = det_lu<E>(Am);
     if (fabs(detA) >= 1e-3) {
         solve_lu<E>(Am, bv, sol);
@@ -365,24 +379,31 @@ __global__ void k_mdbc_gather(const typename Lay<T, D>::TA *__restrict__ A, cons
     using L = Lay<T, D>;
     constexpr int E = D + 1;
     if (ctl->error || ctl->done) return;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        has_new[i] = 0;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    // one warp per particle (every lane reads the same ghost point: the branches below are warp-uniform)
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {
         T gp[D];
         L::getv(ghost[i], gp);
         bool zero = true;
 #pragma unroll
         for (int k = 0; k < D; ++k) zero &= (gp[k] == T(0));
-        if (zero) continue;   // Q10 sentinel: "no ghost node"
+        if (zero) {   // Q10 sentinel: "no ghost node"
+            if (lane == 0) has_new[i] = 0;
+            continue;
+        }
         int bad = 0;
         int gc[3] = {0, 0, 0};
 #pragma unroll
         for (int k = 0; k < D; ++k) gc[k] = map_floor_dev((double)gp[k], inv_cutoff, bad);
         double sol[E];
-        if (!mdbc_node_solve<T, D>(A, type, cell_start, grid, am, ph, gc, gp, sol)) continue;
+        const int ok = mdbc_node_solve<T, D>(A, type, cell_start, grid, am, ph, gc, gp, sol);
+        if (lane != 0) continue;
+        has_new[i] = (uint8_t)ok;
+        if (!ok) continue;
         T xi[D];
         L::pos(A[i], xi);
         rho_new[i] = mdbc_extrapolate<T, D>(sol, xi, gp, ph.rho0);
-        has_new[i] = 1;
     }
 }
 
@@ -403,10 +424,12 @@ __global__ void k_mdbc_nodes(const typename Lay<T, D>::TA *__restrict__ A, const
     using L = Lay<T, D>;
     constexpr int E = D + 1;
     if (ctl->error || ctl->done) return;
-    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < ng; g += nwarps) {
         double *o = out + (size_t)g * (E + 1);
-#pragma unroll
-        for (int k = 0; k <= E; ++k) o[k] = 0.0;
+        if (lane <= E) o[lane] = 0.0;
+        __syncwarp();
         T gp[D];
         L::getv(g_point[g], gp);
         int bad = 0;
@@ -416,9 +439,11 @@ __global__ void k_mdbc_nodes(const typename Lay<T, D>::TA *__restrict__ A, const
         if (gc[am.ax_s] < own_lo || gc[am.ax_s] >= own_hi) continue;   // another rank's node
         double sol[E];
         if (!mdbc_node_solve<T, D>(A, type, cell_start, grid, am, ph, gc, gp, sol)) continue;
-        o[0] = 1.0;
+        if (lane == 0) {
+            o[0] = 1.0;
 #pragma unroll
-        for (int k = 0; k < E; ++k) o[k + 1] = sol[k];
+            for (int k = 0; k < E; ++k) o[k + 1] = sol[k];
+        }
     }
 }
 

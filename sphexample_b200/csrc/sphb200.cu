@@ -239,6 +239,7 @@ class Sim final : public sphb200_sim {
     int opt_lists, opt_lcap, opt_list_smem_kb;   // per-particle neighbour lists (sph_ring.cuh)
     int opt_list_reorder;                        // bank-aware entry order (sph_listorder.h, k_list_reorder)
     int opt_list_local;                          // per-brick list validity (brick_list_decision) instead of one global bound
+    int opt_list_local_auto = 1;                 // ... chosen at upload from the particle count unless set explicitly
     int opt_verify_lists = 0;                    // test hook: count listed-pair misses before every pass (k_list_verify)
     int opt_list_lookahead = 3;                  // bricks due within this many steps are rebuilt along with the urgent ones
     int opt_build_smem_kb = 10;                  // staged positions per stage of k_list_build (r3b: 8-14 KB -> 2.76-2.80 ms first step, 24 KB 2.99)
@@ -298,6 +299,9 @@ class Sim final : public sphb200_sim {
         // measured on B200 (profiles/r2r_configs.jsonl): the conditional nodes cost as much as the ~17 empty
         // kernels they replace (C1 57 vs 60, C2 304 vs 317, C5 19.6 vs 20.4 Mpu/s) — off by default
         opt_graph_cond = env_int("SPHB200_GRAPH_COND", 0);
+        // measured on B200 (profiles/r4b_small_launches.txt): an empty predicated kernel costs 2.4 us, the 13 of the
+        // UpdateNeighbors! chain a third of a C1 step -> steps that will not rebuild replay a graph without the chain
+        opt_lean = env_int("SPHB200_LEAN", 1);
         // lists: fp32 only by default (an fp64 3D window does not fit shared memory), never with
         // PlanarShifting (the shifting displacement is not covered by the |v| dt bound)
         // (2D fp64 windows fit too: C2 186 -> 325 Mpu/s, profiles/r1m_configs.jsonl)
@@ -306,7 +310,12 @@ class Sim final : public sphb200_sim {
         opt_list_smem_kb = env_int("SPHB200_LIST_SMEM_KB", 0);    // > 0: pretend a ring slot holds only this much (tests of the overflow fallback)
         opt_skin = env_int("SPHB200_SKIN_PCT", 4) * 0.01;       // r2q sweep with per-brick rebuilds: 3 % .. 10 % -> 871 / 874 / 867 / 858 / 848 / 818 Mpu/s
         opt_list_reorder = env_int("SPHB200_LIST_REORDER", 1);
-        opt_list_local = env_int("SPHB200_LIST_LOCAL", 1);
+        // per-brick maintenance costs two latency-bound kernels per step (~17 us) and saves most of the list
+        // builds: worth it at 1 M particles (815 -> 874 Mpu/s, profiles/r2n), a loss on the small cases (C1 80 vs
+        // 92, C2 369 vs 405, C5 36 vs 40 Mpu/s, profiles/r4c_small_profile*.jsonl) -> chosen at upload by size
+        opt_list_local = env_int("SPHB200_LIST_LOCAL", -1);
+        opt_list_local_auto = opt_list_local < 0;
+        if (opt_list_local_auto) opt_list_local = 1;
         opt_list_lookahead = env_int("SPHB200_LIST_LOOKAHEAD", 3);
         am.ax_f = 0;       // default: the reference's own cell order (x fastest, last component most significant)
         am.ax_s = D - 1;
@@ -397,6 +406,8 @@ class Sim final : public sphb200_sim {
         drop_step_graph();
         if (k == "graph") { opt_graph = (int)value; return SPHB200_OK; }
         if (k == "graph_cond") { opt_graph_cond = (int)value; return SPHB200_OK; }
+        if (k == "lean") { opt_lean = (int)value; return SPHB200_OK; }
+        if (k == "split") { opt_split = (int)value; return SPHB200_OK; }
         if (k == "compact") opt_compact = (int)value;
         else if (k == "tma") opt_tma = (int)value;
         else if (k == "smem_kb") opt_smem_kb = (int)value;
@@ -407,7 +418,7 @@ class Sim final : public sphb200_sim {
         else if (k == "lcap") opt_lcap = std::max(8, ((int)value + 7) & ~7);
         else if (k == "list_smem_kb") opt_list_smem_kb = (int)value;
         else if (k == "list_reorder") opt_list_reorder = (int)value;
-        else if (k == "list_local") opt_list_local = (int)value;
+        else if (k == "list_local") { opt_list_local = (int)value; opt_list_local_auto = 0; }
         else if (k == "verify_lists") opt_verify_lists = (int)value;
         else if (k == "list_lookahead") opt_list_lookahead = std::max(0, (int)value);
         else if (k == "build_smem_kb") opt_build_smem_kb = std::max(8, (int)value);
@@ -422,7 +433,9 @@ class Sim final : public sphb200_sim {
         CK(cudaSetDevice(device));
         int rc = sync_ctl();
         if (rc) return rc;
-        if (k == "list_builds") *value = h_ctl->list_build_equiv;        // in units of "every brick once"
+        if (k == "lean_steps") *value = (double)n_lean_steps;       // steps replayed without the UpdateNeighbors! chain
+        else if (k == "lean_pauses") *value = (double)n_lean_pauses;   // ... of which had to be finished with it after all
+        else if (k == "list_builds") *value = h_ctl->list_build_equiv;        // in units of "every brick once"
         else if (k == "list_build_steps") *value = h_ctl->n_list_builds;   // steps in which at least one brick was rebuilt
         else if (k == "list_missing") *value = (double)h_ctl->list_missing;
         else if (k == "list_off") *value = h_ctl->list_off || h_ctl->list_fail;
@@ -534,7 +547,9 @@ class Sim final : public sphb200_sim {
         if (count < 1 || count > (int64_t)INT_MAX / 8 || !pos || !rho || !ty)
             return fail(SPHB200_EINVAL, "upload: need n >= 1, position, density and type");
         CK(cudaSetDevice(device));
-        drop_step_graph();   // n is a kernel argument
+        if (count != n) drop_step_graph();   // n is a kernel argument (a re-upload of the same size keeps the captured steps:
+                                             // buffers, counts and options are what they were; reallocations drop them themselves)
+        if (opt_list_local_auto) opt_list_local = count >= 131072 ? 1 : 0;
         int rc = alloc_particles(count);
         if (rc) return rc;
         if ((rc = ensure_lists())) return rc;
@@ -906,10 +921,19 @@ class Sim final : public sphb200_sim {
         return blocks;
     }
     // the list kernel: one persistent CTA per SM (producer warp + consumer warps over a ring of windows)
+    // fp64, few particles: 4 lanes per target (k_interact_ring, SPLIT) — below ~32 k particles there are fewer
+    // 32-target sub-bricks than consumer warps on the GPU, and a pass is as long as one lane's walk of its list
+    bool ring_split() const {
+        if (sizeof(T) != 8 || generic) return false;
+        return opt_split < 0 ? n <= 32768 : opt_split != 0;
+    }
     template <int PASS, bool GEN>
     int launch_ring_t(int epilogue) {
         using RG = RingGeom<T, D, GEN>;
         auto kern = k_interact_ring<T, D, PASS, GEN>;
+        if constexpr (std::is_same<T, double>::value && !GEN && D == 2) {
+            if (ring_split()) kern = k_interact_ring<T, D, PASS, GEN, 4>;
+        }
         int ctas = 0, rc;
         if ((rc = configure_kernel(kern, RG::THREADS, RG::SMEM, &ctas))) return rc;
         InteractArgs<T, D> g;
@@ -1026,7 +1050,7 @@ class Sim final : public sphb200_sim {
     int enqueue_mdbc() {
         if (slab.active) return slab_enqueue_mdbc();
         const int nn = (int)n;
-        k_mdbc_gather<T, D><<<grid_for(nn, 128), 128, 0, stream>>>(A.p, ghost.p, type.p, cell_start.p, d_grid.p, am, nn, ph,
+        k_mdbc_gather<T, D><<<grid_for((int64_t)nn * 32, 128), 128, 0, stream>>>(A.p, ghost.p, type.p, cell_start.p, d_grid.p, am, nn, ph,
                                                                    prm.H_inv, rho_new.p, has_new.p, d_ctl.p);
         k_mdbc_apply<T, D><<<grid_for(nn), 256, 0, stream>>>(A.p, RN.p, type.p, rho_new.p, has_new.p, nn, d_ctl.p);
         launches += 2;
@@ -1121,11 +1145,22 @@ class Sim final : public sphb200_sim {
     int opt_graph_cond = 0;   // UpdateNeighbors! and the list maintenance behind CUDA-graph conditional (IF) nodes
     cudaGraphConditionalHandle cond_rebuild = 0, cond_lists = 0;   // non-zero only while a conditional step graph is captured / alive
     bool capturing_cond = false;   // the handles are kernel arguments ONLY inside that graph (plain launches must not touch them)
+    // the lean step (no reductions sweep, no UpdateNeighbors! chain; k_step_control pauses a step that needs the chain)
+    cudaGraph_t lean_graph = nullptr;
+    cudaGraphExec_t lean_exec = nullptr;
+    int64_t lean_graph_launches = 0;
+    int opt_lean = 1;
+    int opt_split = env_int("SPHB200_SPLIT", -1);   // list kernel, fp64 2D: 4 lanes per target (-1: by particle count)
+    int64_t n_lean_steps = 0, n_lean_pauses = 0;
     void drop_step_graph() {
         if (step_exec) cudaGraphExecDestroy(step_exec);
         if (step_graph) cudaGraphDestroy(step_graph);
         step_exec = nullptr;
         step_graph = nullptr;
+        if (lean_exec) cudaGraphExecDestroy(lean_exec);
+        if (lean_graph) cudaGraphDestroy(lean_graph);
+        lean_exec = nullptr;
+        lean_graph = nullptr;
         cond_rebuild = cond_lists = 0;
     }
     // The step as ONE graph whose rarely needed parts sit behind conditional nodes:
@@ -1244,6 +1279,56 @@ class Sim final : public sphb200_sim {
         return SPHB200_OK;
     }
 
+    // One lean step: S0/S1 come from the previous pass 2 (ctl->red_ready, checked by the caller), no
+    // UpdateNeighbors! chain — k_step_control pauses the step if it turns out to need one.
+    int enqueue_lean_sequence() {
+        int rc;
+        k_step_control<T><<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, ph.h, ph.c0, (T)prm.cfl, lists_on() ? opt_skin * prm.H : 0.0,
+                                               motion_vmax(), 1, opt_list_local, 0ull, 0ull);
+        ++launches;
+        CK(cudaGetLastError());
+        if ((rc = enqueue_body_pre())) return rc;
+        if ((rc = enqueue_list_build())) return rc;
+        return enqueue_body_passes();
+    }
+    int enqueue_step_lean() {
+        int rc;
+        if ((rc = ensure_lists())) return rc;
+        ++n_lean_steps;
+        if (!opt_graph || stream == nullptr) return enqueue_lean_sequence();
+        if (!lean_exec) {
+            const int64_t l0 = launches;
+            if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                cudaGetLastError();
+                opt_graph = 0;
+                return enqueue_lean_sequence();
+            }
+            rc = enqueue_lean_sequence();
+            cudaError_t e = cudaStreamEndCapture(stream, &lean_graph);
+            if (rc || e != cudaSuccess) {
+                drop_step_graph();
+                return rc ? rc : fail(SPHB200_ECUDA, "lean step graph capture failed: %s", cudaGetErrorString(e));
+            }
+            CK(cudaGraphInstantiate(&lean_exec, lean_graph, 0));
+            lean_graph_launches = launches - l0;
+            launches = l0;
+        }
+        CK(cudaGraphLaunch(lean_exec, stream));
+        launches += lean_graph_launches;
+        return SPHB200_OK;
+    }
+    // how many of the next steps can go without UpdateNeighbors!, from the host's copy of the control block:
+    // delta_x grows by about last_disp4 per step and triggers at h (step_control); 0 = the next step rebuilds
+    int64_t lean_steps_ahead() const {
+        if (!opt_lean || !have_cells || !have_half || !h_ctl->red_ready || h_ctl->done || h_ctl->error) return 0;
+        const double room = (double)ph.h - h_ctl->delta_x;
+        if (!(room > 0.0)) return 0;
+        const double d = h_ctl->last_disp4;
+        if (!(d > 0.0)) return opt_batch;
+        const double k = 0.9 * room / d - 1.0;
+        return k < 1.0 ? 0 : (int64_t)std::min<double>(k, (double)opt_batch);
+    }
+
     int run_steps(int64_t nsteps, bool until_target) {
         if (!uploaded) return fail(SPHB200_ESTATE, "step before upload");
         CK(cudaSetDevice(device));
@@ -1261,9 +1346,31 @@ class Sim final : public sphb200_sim {
             } else {
                 batch = 1;
             }
-            for (int64_t s = 0; s < batch; ++s)
-                if ((rc = enqueue_step())) return rc;
-            if ((rc = sync_ctl())) return rc;
+            if (opt_lean) {
+                const int64_t ahead = lean_steps_ahead();
+                if (ahead >= 1) {
+                    batch = std::min(batch, ahead);
+                    for (int64_t s = 0; s < batch; ++s)
+                        if ((rc = enqueue_step_lean())) return rc;
+                } else {
+                    if ((rc = enqueue_step())) return rc;      // the full sequence (it may rebuild), one step, then look again
+                }
+                if ((rc = sync_ctl())) return rc;
+                if (h_ctl->paused && !h_ctl->error) {
+                    // a lean step found that it has to rebuild after all: its control part is done, the rest of the
+                    // batch ran empty behind it; finish it with the full body (UpdateNeighbors! included)
+                    ++n_lean_pauses;
+                    h_ctl->paused = 0;
+                    h_ctl->done = 0;
+                    if ((rc = push_ctl())) return rc;
+                    if ((rc = enqueue_step_body())) return rc;
+                    if ((rc = sync_ctl())) return rc;
+                }
+            } else {
+                for (int64_t s = 0; s < batch; ++s)
+                    if ((rc = enqueue_step())) return rc;
+                if ((rc = sync_ctl())) return rc;
+            }
             for (int attempt = 0; h_ctl->error == SPHB200_ECAPACITY; ++attempt) {
                 if (attempt >= 3) return fail(SPHB200_ECAPACITY, "cell grid / brick list capacity exceeded");
                 if ((rc = recover_capacity())) return rc;
