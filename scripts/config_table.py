@@ -76,11 +76,7 @@ def row(name, case, steps, warm, cpu_steps, **opts):
 
 P = lambda c: util.perturb(c, vel_scale=1.0)   # a moving state: from rest the velocities are ~0 and relative errors meaningless
 row("C1 2D dam break shipped (6 881), fp64", P(util.case_c1("float64")), 400, 20, 40)
-row("C1 flat step graph (no conditional nodes)", P(util.case_c1("float64")), 400, 20, 40, graph_cond=0)
-row("C1 cull kernel only, no step graph", P(util.case_c1("float64")), 400, 20, 40, lists=0, graph=0)
+row("C1 full step sequence, whole-list lanes (round-2 start)", P(util.case_c1("float64")), 400, 20, 40, lean=0, split=0, list_local=1)
 row("C2 2D dam break dp=0.0058 (59 909), fp64", P(cases.case_dam_break_2d(0.0058, "float64")), 400, 20, 10)
-row("C2 flat step graph (no conditional nodes)", P(cases.case_dam_break_2d(0.0058, "float64")), 400, 20, 10, graph_cond=0)
-row("C2 no step graph", P(cases.case_dam_break_2d(0.0058, "float64")), 400, 20, 10, graph=0)
 row("C5 StillWedge mDBC (3 027), fp64", util.case_c5("float64"), 400, 20, 40)
-row("C5 flat step graph (no conditional nodes)", util.case_c5("float64"), 400, 20, 40, graph_cond=0)
 row("3D dam break, the shipped 171 496-particle files, fp32", P(util.case_3d_shipped("float32")), 200, 20, 5)

@@ -56,7 +56,8 @@ struct Ctl {
     long long list_missing;    // test hook (option verify_lists): pairs within H found missing from a list in use
     // lean step sequence (single GPU): the captured step holds no UpdateNeighbors! chain; a step that needs one
     // pauses itself (done = 1, paused = 1) and the host runs its body with the chain
-    int paused;
+    int paused;                // 1: paused at the step head (nothing of the body has run); 2: paused after a failed list build
+                               //    (motion, mDBC and the list build have run; the passes have not)
     double last_disp4;         // what the last step head added to delta_x (4 x the largest half-step displacement)
 };
 
@@ -227,7 +228,10 @@ SPH_HD void step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, double list
             }
         }
     }
-    if (pause_on_rebuild && ctl->do_rebuild) {
+    // pause bits: 1 = the captured sequence holds no UpdateNeighbors! chain; 2 = nor the cull kernels (a pass
+    // that is not served by the lists needs the full sequence as well)
+    if (((pause_on_rebuild & 1) && ctl->do_rebuild) ||
+        ((pause_on_rebuild & 2) && (ctl->list_mode[0] != 2 || ctl->list_mode[1] != 2))) {
         ctl->done = 1;
         ctl->paused = 1;
     }

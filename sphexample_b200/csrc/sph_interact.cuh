@@ -96,6 +96,7 @@ struct InteractArgs {
     float *brick_move;                 // per brick: accumulated relative-displacement bound (reset by the build)
     T Hs2;                             // (H + skin)^2: acceptance radius of a list build
     int force_cull;                    // 1: ignore ctl->list_mode (stage-level entry points)
+    int lean_guard;                    // 1: no cull kernel stands by in this sequence — a failed list build pauses the step
 };
 
 // ctl->list_mode[pass]: which kernel serves the pass

@@ -745,7 +745,15 @@ __global__ void __launch_bounds__(RingGeom<T, D, GENERIC>::THREADS, 1) k_interac
     static_assert(OFF_BN + CAP * SS::esBn <= RG::SLOT_BYTES, "ring slot too small");
 
     if (g.ctl->error || g.ctl->done) return;
-    if (g.ctl->list_mode[PASS] != LM_USE || g.ctl->list_fail) return;
+    if (g.ctl->list_mode[PASS] != LM_USE || g.ctl->list_fail) {
+        // lean sequence (no cull kernel behind this one): this step's list build overflowed — stop the step here;
+        // the host finishes it with the full sequence.  (Every CTA returns whether or not it sees `done` yet.)
+        if (PASS == 0 && g.lean_guard && g.ctl->list_fail && blockIdx.x == 0 && threadIdx.x == 0) {
+            g.ctl->paused = 2;
+            g.ctl->done = 1;
+        }
+        return;
+    }
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_full[NSLOT], s_empty[NSLOT];

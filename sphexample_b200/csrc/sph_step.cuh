@@ -111,7 +111,7 @@ __global__ void k_step_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, doubl
 }
 
 // UpdateMetaData!, src/SPHCellList.jl:679-685 (S19) (+ the list-maintenance accounting of the step)
-__global__ void k_step_end(Ctl *ctl, const GridInfo *grid) {
+__device__ __forceinline__ void step_end_full(Ctl *ctl, const GridInfo *grid) {
     if (!(ctl->error || ctl->done || !ctl->step_open) && ctl->bricks_flagged > 0) {
         ctl->list_build_equiv += (double)ctl->bricks_flagged / (double)max(1, grid->nbricks);
         ctl->n_list_builds += 1;
@@ -119,6 +119,21 @@ __global__ void k_step_end(Ctl *ctl, const GridInfo *grid) {
     ctl->bricks_flagged = 0;
     ctl->bricks_urgent = 0;
     step_end(ctl);
+}
+__global__ void k_step_end(Ctl *ctl, const GridInfo *grid) { step_end_full(ctl, grid); }
+
+// lean sequence: S19 of the previous step (if it is still open) and the head of the next one in ONE
+// one-thread kernel — between two lean steps nothing else happens (the batch ends with a k_step_end)
+template <class T>
+__global__ void k_step_end_control(Ctl *ctl, GridInfo *grid, T h, T c0, T cfl, double list_skin, double motion_vmax,
+                                   int pause_bits, int list_local) {
+    step_end_full(ctl, grid);
+    step_control<T>(ctl, grid, h, c0, cfl, list_skin, motion_vmax, pause_bits, list_local);
+}
+
+// test hook (option test_fail_list_build_at): pretend this step's list build overflowed
+__global__ void k_test_fail_list_build(Ctl *ctl) {
+    if (!ctl->error && !ctl->done) ctl->list_fail |= 2;
 }
 
 // any change of positions or cells outside the step sequence voids the neighbour lists

@@ -408,6 +408,7 @@ class Sim final : public sphb200_sim {
         if (k == "graph_cond") { opt_graph_cond = (int)value; return SPHB200_OK; }
         if (k == "lean") { opt_lean = (int)value; return SPHB200_OK; }
         if (k == "split") { opt_split = (int)value; return SPHB200_OK; }
+        if (k == "test_fail_list_build_at") { opt_test_fail_at = (int64_t)value; return SPHB200_OK; }   // n-th lean step (graph off)
         if (k == "compact") opt_compact = (int)value;
         else if (k == "tma") opt_tma = (int)value;
         else if (k == "smem_kb") opt_smem_kb = (int)value;
@@ -896,6 +897,7 @@ class Sim final : public sphb200_sim {
         const double Hs = prm.H * (1.0 + opt_skin);
         g.Hs2 = (T)(Hs * Hs);
         g.force_cull = cull_force;
+        g.lean_guard = lean_enqueue ? 1 : 0;
     }
     // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) + occupancy, once per kernel, smem size and HANDLE
     // (the attribute is per device; a handle is bound to one device)
@@ -1020,7 +1022,7 @@ class Sim final : public sphb200_sim {
                 else k_list_verify<T, D, false, BT><<<num_sms * 2, BT, 0, stream>>>(g, pass);
                 ++launches;
             }
-            if ((rc = launch_cull(pass, epilogue, 0))) return rc;
+            if (!lean_enqueue && (rc = launch_cull(pass, epilogue, 0))) return rc;   // (lean: see enqueue_lean_sequence)
             if (generic) return pass ? launch_ring_t<1, true>(epilogue) : launch_ring_t<0, true>(epilogue);
             return pass ? launch_ring_t<1, false>(epilogue) : launch_ring_t<0, false>(epilogue);
         }
@@ -1090,7 +1092,7 @@ class Sim final : public sphb200_sim {
         if (prm.mdbc && (rc = enqueue_mdbc())) return rc;                     // S6  "04 Apply MDBC before Half TimeStep"
         return SPHB200_OK;
     }
-    int enqueue_body_passes(cudaEvent_t *ev = nullptr) {
+    int enqueue_body_passes(cudaEvent_t *ev = nullptr, bool with_end = true) {
         int rc;
         if ((rc = launch_interact(0, EPI_FUSED))) return rc;                  // S4-S10, S13  "05", "03", "06", "07"
         if (ev) CK(cudaEventRecord(ev[5], stream));
@@ -1098,8 +1100,10 @@ class Sim final : public sphb200_sim {
         if (ev) CK(cudaEventRecord(ev[6], stream));
         if ((rc = launch_interact(1, EPI_FUSED))) return rc;                  // S11, S14-S18  "08", "03", "09", "10", "11"
         if (ev) CK(cudaEventRecord(ev[7], stream));
-        k_step_end<<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p);                   // S19 "12 Update MetaData"
-        ++launches;
+        if (with_end) {
+            k_step_end<<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p);               // S19 "12 Update MetaData"
+            ++launches;
+        }
         CK(cudaGetLastError());
         have_half = true;
         have_cells = true;
@@ -1151,7 +1155,7 @@ class Sim final : public sphb200_sim {
     int64_t lean_graph_launches = 0;
     int opt_lean = 1;
     int opt_split = env_int("SPHB200_SPLIT", -1);   // list kernel, fp64 2D: 4 lanes per target (-1: by particle count)
-    int64_t n_lean_steps = 0, n_lean_pauses = 0;
+    int64_t n_lean_steps = 0, n_lean_pauses = 0, opt_test_fail_at = 0;
     void drop_step_graph() {
         if (step_exec) cudaGraphExecDestroy(step_exec);
         if (step_graph) cudaGraphDestroy(step_graph);
@@ -1279,17 +1283,27 @@ class Sim final : public sphb200_sim {
         return SPHB200_OK;
     }
 
-    // One lean step: S0/S1 come from the previous pass 2 (ctl->red_ready, checked by the caller), no
-    // UpdateNeighbors! chain — k_step_control pauses the step if it turns out to need one.
+    // One lean step: S0/S1 come from the previous pass 2 (ctl->red_ready, checked by the caller); no
+    // UpdateNeighbors! chain and, with lists, no cull kernels standing by — the step control pauses a step that
+    // turns out to need either (ctl->paused = 1), the list kernel one whose list build overflowed (paused = 2).
+    // S19 of a lean step rides in the head kernel of the next one; the caller closes the batch with k_step_end.
+    bool lean_enqueue = false;
     int enqueue_lean_sequence() {
         int rc;
-        k_step_control<T><<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, ph.h, ph.c0, (T)prm.cfl, lists_on() ? opt_skin * prm.H : 0.0,
-                                               motion_vmax(), 1, opt_list_local, 0ull, 0ull);
+        k_step_end_control<T><<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, ph.h, ph.c0, (T)prm.cfl, lists_on() ? opt_skin * prm.H : 0.0,
+                                                   motion_vmax(), lists_on() ? 3 : 1, opt_list_local);
         ++launches;
         CK(cudaGetLastError());
         if ((rc = enqueue_body_pre())) return rc;
         if ((rc = enqueue_list_build())) return rc;
-        return enqueue_body_passes();
+        if (opt_test_fail_at > 0 && n_lean_steps == opt_test_fail_at && lists_on()) {   // test hook (plain launches only)
+            k_test_fail_list_build<<<1, 1, 0, stream>>>(d_ctl.p);
+            ++launches;
+        }
+        lean_enqueue = lists_on();
+        rc = enqueue_body_passes(nullptr, false);
+        lean_enqueue = false;
+        return rc;
     }
     int enqueue_step_lean() {
         int rc;
@@ -1321,6 +1335,12 @@ class Sim final : public sphb200_sim {
     // delta_x grows by about last_disp4 per step and triggers at h (step_control); 0 = the next step rebuilds
     int64_t lean_steps_ahead() const {
         if (!opt_lean || !have_cells || !have_half || !h_ctl->red_ready || h_ctl->done || h_ctl->error) return 0;
+        if (lists_on()) {
+            // the lean sequence has no cull kernels: while the lists are off (after an overflow) or the half-step
+            // displacement is about to outgrow the skin (pass 2 falls back to the cull kernel), take full steps
+            if (h_ctl->list_off || h_ctl->list_fail || !h_ctl->list_valid) return 0;
+            if (h_ctl->dt2 * h_ctl->vmax_now > 0.9 * 0.49 * opt_skin * prm.H) return 0;
+        }
         const double room = (double)ph.h - h_ctl->delta_x;
         if (!(room > 0.0)) return 0;
         const double d = h_ctl->last_disp4;
@@ -1352,6 +1372,8 @@ class Sim final : public sphb200_sim {
                     batch = std::min(batch, ahead);
                     for (int64_t s = 0; s < batch; ++s)
                         if ((rc = enqueue_step_lean())) return rc;
+                    k_step_end<<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p);   // S19 of the batch's last step
+                    ++launches;
                 } else {
                     if ((rc = enqueue_step())) return rc;      // the full sequence (it may rebuild), one step, then look again
                 }
@@ -1360,10 +1382,13 @@ class Sim final : public sphb200_sim {
                     // a lean step found that it has to rebuild after all: its control part is done, the rest of the
                     // batch ran empty behind it; finish it with the full body (UpdateNeighbors! included)
                     ++n_lean_pauses;
+                    const int where = h_ctl->paused;
                     h_ctl->paused = 0;
                     h_ctl->done = 0;
                     if ((rc = push_ctl())) return rc;
-                    if ((rc = enqueue_step_body())) return rc;
+                    if (where == 2) rc = enqueue_body_passes();   // motion, mDBC and the (failed) list build have run
+                    else rc = enqueue_step_body();
+                    if (rc) return rc;
                     if ((rc = sync_ctl())) return rc;
                 }
             } else {

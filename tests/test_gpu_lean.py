@@ -60,6 +60,25 @@ def test_a_mispredicted_lean_step_pauses_and_is_finished_with_the_rebuild():
     assert sb["lean_steps"] > 400
 
 
+def test_a_list_build_that_fails_inside_a_lean_step_pauses_it_before_the_passes():
+    """the lean sequence has no cull kernels standing by: when the step's own list build overflows, the list
+    kernel stops the step (ctl->paused = 2) and the host runs the two passes with the full sequence — the cull
+    kernels — after which the lists stay off until the next cell rebuild (test hook: the overflow is injected)"""
+    mk = lambda: util.perturb(util.case_c1("float64"), vel_scale=1.0)
+    a, ra, sa = _run(mk(), 60, [60], lean=0)
+    sim = Simulation(util.params_of(mk()))
+    for k, v in (("lean", 1), ("graph", 0), ("test_fail_list_build_at", 12)):
+        sim.set_option(k, v)
+    sim.upload(mk().particles)
+    rep = sim.step(60, reset_delta_x=True)
+    b = sim.download(order="id")
+    assert sim.stat("lean_pauses") >= 1 and sim.stat("list_fail_reason") == 2 and sim.stat("lean_steps") >= 12
+    sim.close()
+    assert rep["iteration"] == 60 and rep["n_rebuilds"] == ra["n_rebuilds"] and rep["total_time"] == pytest.approx(ra["total_time"], rel=1e-12)
+    for k in ("Position", "Velocity", "Density"):
+        util.check(util.relerr(b[k], a[k]), 1e-10)      # cull and list kernels sum the same pairs in another order
+
+
 def test_simulation_loop_target_time_with_the_lean_sequence():
     case = util.perturb(util.case_c1("float64"), vel_scale=1.0)
     out = []
