@@ -297,3 +297,58 @@ def SetupVTKOutput(save_location: str, simulation_name: str, export_single: bool
             tr["w"].close()
 
     return save_particles, close_files
+
+
+def compute_grid_geometry(H: float, unique_cells: np.ndarray):
+    """`compute_grid_geometry` (src/ProduceHDFVTK.jl:38-118): the occupied cells (UniqueCells[n, D], integer cell
+    coordinates; cell c is centred on c·H, edge H) as VTK quads (2D, type 9) / hexahedra (3D, type 12).  Returns
+    (points[n·2^D, 3], connectivity, offsets, cell_types, cell_data) — cell_data = the 1-based linear index of the
+    cell in the bounding box of the occupied cells, x fastest."""
+    cells = np.asarray(unique_cells, np.int64)
+    n, D = cells.shape
+    if D not in (2, 3):
+        raise ValueError(f"Dimensionality of UniqueCells must be 2 or 3, got {D}")
+    lo = cells.min(axis=0) if n else np.zeros(D, np.int64)
+    ext = (cells.max(axis=0) - lo + 1) if n else np.ones(D, np.int64)
+    idx = cells - lo
+    cell_data = (idx[:, 1] * ext[0] + idx[:, 0] + 1) if D == 2 else ((idx[:, 2] * ext[1] + idx[:, 1]) * ext[0] + idx[:, 0] + 1)
+    sx = np.array([-1, 1, 1, -1], np.float64)
+    sy = np.array([-1, -1, 1, 1], np.float64)
+    c = cells.astype(np.float64) * H
+    if D == 2:
+        pts = np.zeros((n, 4, 3))
+        pts[:, :, 0] = c[:, None, 0] + sx * (H / 2)
+        pts[:, :, 1] = c[:, None, 1] + sy * (H / 2)
+        vtk_type = 9
+    else:
+        pts = np.zeros((n, 8, 3))
+        pts[:, :, 0] = c[:, None, 0] + np.tile(sx, 2) * (H / 2)
+        pts[:, :, 1] = c[:, None, 1] + np.tile(sy, 2) * (H / 2)
+        pts[:, :, 2] = c[:, None, 2] + np.repeat([-1.0, 1.0], 4) * (H / 2)
+        vtk_type = 12
+    nc = pts.shape[1]
+    points = pts.reshape(n * nc, 3)
+    connectivity = np.arange(n * nc, dtype=np.int64)
+    offsets = np.arange(n + 1, dtype=np.int64) * nc
+    return points, connectivity, offsets, np.full(n, vtk_type, np.uint8), cell_data.astype(np.int64)
+
+
+def SaveCellGridVTKHDF(filepath: str, H: float, unique_cells: np.ndarray) -> int:
+    """`SaveCellGridVTKHDF` (src/ProduceHDFVTK.jl:416-452): the cell list as a static UnstructuredGrid file.
+    `unique_cells` = the occupied cells, e.g. `Simulation.cell_list()[0]`."""
+    from . import hdf5_min as h5
+    points, connectivity, offsets, cell_types, cell_data = compute_grid_geometry(H, unique_cells)
+    root = h5.Group()
+    g = root.group("VTKHDF")
+    g.attrs["Version"] = np.array([2, 3], np.int64)
+    g.attrs["Type"] = b"UnstructuredGrid"
+    g.dataset("NumberOfPoints", np.array([points.shape[0]], np.int64))
+    g.dataset("NumberOfCells", np.array([cell_types.shape[0]], np.int64))
+    g.dataset("NumberOfConnectivityIds", np.array([connectivity.shape[0]], np.int64))
+    g.dataset("Points", points)
+    g.dataset("Connectivity", connectivity)
+    g.dataset("Offsets", offsets)
+    g.dataset("Types", cell_types)
+    g.group("CellData").dataset("CellData", cell_data)
+    g.group("FieldData")
+    return h5.write_file(filepath, root)

@@ -157,7 +157,7 @@ extern "C" void shim_control_trace(int n, const double *disp2, const double *vis
         double *t = trace + (size_t)s * 10;
         t[0] = ctl.dt; t[1] = ctl.do_rebuild; t[2] = ctl.list_build; t[3] = ctl.list_mode[0]; t[4] = ctl.list_mode[1];
         t[5] = ctl.done; t[6] = ctl.list_move; t[7] = ctl.delta_x; t[9] = ctl.list_off;
-        if (ctl.done && ctl.do_rebuild) ctl.done = 0;          // the host resumes a paused step after rebuilding
+        if (ctl.done && ctl.paused) { ctl.done = 0; ctl.paused = 0; }   // the host resumes a paused step (rebuild / full sequence)
         if (ctl.do_rebuild) ctl.do_rebuild = 0;                // k_finish_rebuild
         if (ctl.list_build && build_fails[s]) ctl.list_fail = 2;
         step_end(&ctl);
@@ -209,7 +209,7 @@ extern "C" void shim_ctl_head(void *p, double disp2, double visc, double acc2, d
 }
 extern "C" void shim_ctl_body(void *p) {
     ShimCtl *s = (ShimCtl *)p;
-    if (s->ctl.done && s->ctl.do_rebuild) s->ctl.done = 0;
+    if (s->ctl.done && s->ctl.paused) { s->ctl.done = 0; s->ctl.paused = 0; }
     s->ctl.do_rebuild = 0;
     step_end(&s->ctl);
 }

@@ -107,6 +107,29 @@ def test_slab_mode_pauses_the_step_that_needs_a_rebuild(shim):  # noqa: F811
     assert np.allclose(a["total_time"], b["total_time"])
 
 
+def test_lean_sequence_pauses_whenever_it_lacks_a_kernel_the_step_needs(shim):  # noqa: F811
+    """pause bits 1 | 2 (single-GPU lean sequence: no UpdateNeighbors! chain, no cull kernels): a step pauses
+    exactly when it rebuilds or when one of its passes is not served by the lists; the decisions themselves
+    (dt, rebuilds, list builds, modes) are those of the full sequence"""
+    n = 120
+    rng = np.random.default_rng(5)
+    disp = (0.02 + 0.02 * rng.random(n)) * H
+    vel = np.full(n, 1.0)
+    vel[40:60] = 400.0            # a burst of speed: the half-step displacement outgrows the skin, pass 2 goes to the cull kernel
+    fails = np.zeros(n, np.uint8)
+    fails[75:] = 1                # the next build overflows: lists off until the next cell rebuild
+    kw = dict(fails=fails, skin=0.1 * H, delta_x0=1.0 + H)
+    a = trace(shim, disp ** 2, np.zeros(n), np.ones(n), vel ** 2, pause=0, **kw)
+    b = trace(shim, disp ** 2, np.zeros(n), np.ones(n), vel ** 2, pause=3, **kw)
+    for k in ("dt", "do_rebuild", "list_build", "mode0", "mode1", "delta_x", "list_off"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.allclose(a["total_time"], b["total_time"])
+    need_full = (b["do_rebuild"] == 1) | (b["mode0"] != 2) | (b["mode1"] != 2)
+    assert np.array_equal(b["paused"] == 1, need_full)
+    assert need_full.any() and (~need_full).any() and not a["paused"].any()
+    assert np.any((b["mode1"] != 2) & (b["mode0"] == 2)) and np.any(b["list_off"] == 1)    # both reasons occurred
+
+
 def test_moving_bodies_count_towards_the_bound(shim):  # noqa: F811
     n = 100
     t0 = trace(shim, np.zeros(n), np.zeros(n), np.ones(n), np.zeros(n), skin=0.2 * H)

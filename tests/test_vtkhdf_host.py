@@ -182,3 +182,45 @@ def test_cross_check_with_libhdf5_when_available(tmp_path):
         for nm, arr in zip(names, arrays):
             assert np.array_equal(g["PointData"][nm][...], output.to_3d(arr)), nm
         assert g["Lines/Connectivity"].shape == (0,)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_cell_grid_file_has_the_reference_layout(tmp_path, dim):
+    """SaveCellGridVTKHDF / compute_grid_geometry (src/ProduceHDFVTK.jl:38-118,416-452): one quad / hexahedron per
+    occupied cell, centred on cell·H, corner order of the reference, CellData = linear index in the occupied box"""
+    from sphexample_b200.slab import cell_coord
+    case = util.case_c1("float64") if dim == 2 else util.case_3d_small("float32")
+    H = 1.0 / util.params_of(case).H_inv
+    cc = np.stack([cell_coord(case.particles.Position[:, k], 1.0 / H) for k in range(dim)], axis=1)
+    cells = np.unique(cc, axis=0)
+    path = str(tmp_path / "CellGrid_000001.vtkhdf")
+    output.SaveCellGridVTKHDF(path, H, cells)
+    tree = h5_minread.Reader(path).tree()
+    n, nc = len(cells), 2 ** dim
+    a = tree["/VTKHDF@"]
+    assert a["Version"].tolist() == [2, 3] and bytes(a["Type"]) == b"UnstructuredGrid"
+    assert tree["/VTKHDF/NumberOfPoints"].tolist() == [n * nc] and tree["/VTKHDF/NumberOfCells"].tolist() == [n]
+    assert tree["/VTKHDF/NumberOfConnectivityIds"].tolist() == [n * nc]
+    assert np.array_equal(tree["/VTKHDF/Connectivity"], np.arange(n * nc)) and np.array_equal(tree["/VTKHDF/Offsets"], np.arange(n + 1) * nc)
+    assert tree["/VTKHDF/Types"].dtype == np.uint8 and set(tree["/VTKHDF/Types"].tolist()) == {9 if dim == 2 else 12}
+    pts = tree["/VTKHDF/Points"].reshape(n, nc, 3)
+    assert np.allclose(pts.mean(axis=1)[:, :dim], cells * H, atol=1e-12)                       # centred on cell * H
+    assert np.allclose(pts.max(axis=1)[:, :dim] - pts.min(axis=1)[:, :dim], H)                   # edge H
+    assert np.allclose(pts[:, 0, :dim], cells * H - H / 2) and np.allclose(pts[:, 2, :2], cells[:, :2] * H + H / 2)   # corner order
+    if dim == 2:
+        assert np.all(pts[:, :, 2] == 0)
+    else:
+        assert np.allclose(pts[:, 4, 2], cells[:, 2] * H + H / 2) and np.allclose(pts[:, 3, 2], cells[:, 2] * H - H / 2)
+    cd = tree["/VTKHDF/CellData/CellData"]
+    lo, ext = cells.min(axis=0), cells.max(axis=0) - cells.min(axis=0) + 1
+    k = 5
+    want = ((cells[k, 1] - lo[1]) * ext[0] + cells[k, 0] - lo[0] + 1) if dim == 2 else \
+        (((cells[k, 2] - lo[2]) * ext[1] + cells[k, 1] - lo[1]) * ext[0] + cells[k, 0] - lo[0] + 1)
+    assert cd[k] == want and len(np.unique(cd)) == n and cd.min() >= 1
+    # every particle lies inside the box of its own cell
+    which = {tuple(c): i for i, c in enumerate(cells)}
+    sel = np.arange(0, len(cc), 97)
+    for j in sel:
+        b = pts[which[tuple(cc[j])]]
+        x = case.particles.Position[j].astype(np.float64)
+        assert np.all(x >= b.min(axis=0)[:dim] - 1e-9) and np.all(x <= b.max(axis=0)[:dim] + 1e-9)
