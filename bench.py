@@ -371,7 +371,12 @@ def run_ours(args, rank, world, local_rank):
         ev[k][1].record(stream)
     barrier()
     t1 = time.time()
-    ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    step_ms = [float(a.elapsed_time(b)) for a, b in ev]
+    ms = float(sum(step_ms))
+    srt = sorted(step_ms)
+    # where the K per-step times lie (this rank): a cell rebuild + full list build shows as a few slow steps
+    step_spread = {"min": round(srt[0], 4), "median": round(srt[len(srt) // 2], 4), "max": round(srt[-1], 4),
+                   "slowest": [[int(i), round(step_ms[i], 4)] for i in sorted(range(len(step_ms)), key=lambda i: -step_ms[i])[:3]]}
     launches = sim.launch_count - l0
     rebuilds_timed = int(rep["n_rebuilds"]) - rb0
     list_builds_timed = int(sim.stat("list_builds")) - lb0
@@ -495,6 +500,7 @@ def run_ours(args, rank, world, local_rank):
                 "gpu_launches": int(launches), "roofline": roof, "roofline_fp32": roof32, "e2e": e2e,
                 "stage_ms": stage_ms,
                 "rebuilds_in_timed_region": rebuilds_timed, "list_builds_in_timed_region": list_builds_timed, "dp": dp,
+                "step_ms_spread_rank0": step_spread,
                 "state": prep,
                 "back_to_back": {"value": n * args.steps / (ms_b2b * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_b2b / args.steps,
                                  "note": "same K steps enqueued back to back, warm L2"}}
