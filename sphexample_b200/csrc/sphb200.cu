@@ -408,6 +408,7 @@ class Sim final : public sphb200_sim {
         if (k == "graph_cond") { opt_graph_cond = (int)value; return SPHB200_OK; }
         if (k == "lean") { opt_lean = (int)value; return SPHB200_OK; }
         if (k == "split") { opt_split = (int)value; return SPHB200_OK; }
+        if (k == "brick_targets") { opt_brick_targets = ((int)value + 31) & ~31; return SPHB200_OK; }   // 0 = by particle count (takes effect at the next UpdateNeighbors!)
         if (k == "test_fail_list_build_at") { opt_test_fail_at = (int64_t)value; return SPHB200_OK; }   // n-th lean step (graph off)
         if (k == "compact") opt_compact = (int)value;
         else if (k == "tma") opt_tma = (int)value;
@@ -800,14 +801,14 @@ class Sim final : public sphb200_sim {
                                                      ccoord.p);
         k_copy_table<T, D><<<gp, 256, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, table(true), table(false));
         if (slab.active) {   // boundary-layer bricks first: a pass takes them first and ships their results early
-            k_build_bricks<D><<<grid_for(row_cap, 128), 128, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, BT, brick_window_limit(),
+            k_build_bricks<D><<<grid_for(row_cap, 128), 128, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, brick_targets(), brick_window_limit(),
                                                                            bricks.p, brick_cap, 1);
             k_mark_boundary_bricks<<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p);
-            k_build_bricks<D><<<grid_for(row_cap, 128), 128, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, BT, brick_window_limit(),
+            k_build_bricks<D><<<grid_for(row_cap, 128), 128, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, brick_targets(), brick_window_limit(),
                                                                            bricks.p, brick_cap, 2);
             launches += 2;
         } else {
-            k_build_bricks<D><<<grid_for(row_cap, 128), 128, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, BT, brick_window_limit(),
+            k_build_bricks<D><<<grid_for(row_cap, 128), 128, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, brick_targets(), brick_window_limit(),
                                                                            bricks.p, brick_cap, 0);
         }
         k_finish_rebuild<<<1, 1, 0, stream>>>(d_ctl.p, d_grid.p, cell_start.p, count_rebuild);
@@ -832,6 +833,18 @@ class Sim final : public sphb200_sim {
         if (!lists_on()) return 8192;
         const int lim = list_cap_cand() - 8 - 6 * ((D == 3) ? 9 : 3);   // RingGeom::WINDOW_LIMIT for the effective cap
         return lim >= 64 ? lim : 64;
+    }
+    // Particles per brick (<= BT).  A brick is served by ONE CTA of the list kernel, i.e. one SM: with few particles
+    // the bricks must be small enough to reach every SM several times over — C1 (6 881 particles) is 54 bricks of 128,
+    // so 94 of the 148 SMs idle while the others grind through a brick each on their fp64 pipes
+    // (profiles/r4h_prof_ring_c1_ncu.txt: SMs active 39 % of the kernel).  Halved until there are two bricks per SM —
+    // and no further: once every SM is busy, smaller bricks only add staging (C2, 60 k particles: 425 Mpu/s with
+    // bricks of 128, 332 with 64; C1: 110 -> 148, C5: 48 -> 67 with 32; profiles/r4i_small_profile*.jsonl).
+    int brick_targets() const {
+        if (opt_brick_targets > 0) return std::min(opt_brick_targets, BT);
+        int bt = BT;
+        while (bt > 32 && n / bt < 2 * (int64_t)num_sms) bt >>= 1;
+        return bt;
     }
     double motion_vmax() const {
         double v = 0.0;
@@ -1154,6 +1167,7 @@ class Sim final : public sphb200_sim {
     cudaGraphExec_t lean_exec = nullptr;
     int64_t lean_graph_launches = 0;
     int opt_lean = 1;
+    int opt_brick_targets = env_int("SPHB200_BRICK_TARGETS", 0);
     int opt_split = env_int("SPHB200_SPLIT", -1);   // list kernel, fp64 2D: 4 lanes per target (-1: by particle count)
     int64_t n_lean_steps = 0, n_lean_pauses = 0, opt_test_fail_at = 0;
     void drop_step_graph() {

@@ -141,7 +141,9 @@ def test_bank_ordered_lists_give_the_same_physics(name):
     (r0, s0, b0, off0), (r1, s1, b1, off1) = out[0], out[1]
     assert b0 == b1 >= 2 and off0 == off1 == 0
     assert r0["n_rebuilds"] == r1["n_rebuilds"]
-    tol = 1e-11 if name.endswith("f64") else 6e-6      # measured 2.1e-6
+    # fp32: two runs that differ only in summation order drift apart by rounding noise amplified over 80 steps of a
+    # fast flow — measured 2.1e-6 with bricks of 128 targets, 9.5e-6 with bricks of 32 (another partition = another order)
+    tol = 1e-11 if name.endswith("f64") else 2e-5
     for f in ("Position", "Velocity", "Density"):
         util.check(util.relerr(s1[f], s0[f]), tol)
 
