@@ -501,6 +501,9 @@ def run_ours(args, rank, world, local_rank):
                 "stage_ms": stage_ms,
                 "rebuilds_in_timed_region": rebuilds_timed, "list_builds_in_timed_region": list_builds_timed, "dp": dp,
                 "step_ms_spread_rank0": step_spread,
+                "stage_ms_note": "stage_ms samples the FULL step sequence (sphb200_stage_times: UpdateNeighbors! chain and stand-by "
+                                 "kernels in place, running empty when not needed); on one GPU the timed steps replay the lean "
+                                 "sequence, which has neither, so the stages add up to slightly more than ms_per_step",
                 "state": prep,
                 "back_to_back": {"value": n * args.steps / (ms_b2b * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_b2b / args.steps,
                                  "note": "same K steps enqueued back to back, warm L2"}}

@@ -144,12 +144,16 @@ int sphb200_set_stream(sphb200_sim *sim, void *cuda_stream);
  * "smem_kb" (shared memory per CTA of the cull kernel), "batch" (steps per host sync),
  * "generic" (1 = force the run-time-dispatched pair body), "lists" (0/1 per-particle neighbour
  * lists reused across passes), "skin" (list skin as a fraction of H), "lcap" (list entries per
- * particle), "list_smem_kb" (shared memory per CTA of the list kernel), "list_order" (0/1 bank-aware
- * order of the list entries; experimental), "graph" (0/1 replay one
- * captured CUDA graph per step instead of ~25 launches) */
+ * particle), "list_smem_kb" (shared memory per CTA of the list kernel), "list_reorder" (0/1 bank-aware
+ * order of the list entries), "list_local" (0/1 per-brick instead of global list maintenance; default by
+ * particle count), "graph" (0/1 replay captured CUDA graphs instead of plain launches), "lean" (0/1 steps
+ * that will not rebuild replay a sequence without the UpdateNeighbors! chain), "split" (-1/0/1 list kernel,
+ * 2D fp64: 4 lanes per target; default by particle count), "brick_targets" (particles per brick, <= 128;
+ * 0 = by particle count) */
 int sphb200_set_option(sphb200_sim *sim, const char *name, double value);
 /* run-time counters: "list_builds", "list_off" (1 = lists switched off after an overflow),
- * "halo_bytes_per_step", "migrated", "n_total" (owned + halo particles held) */
+ * "halo_bytes_per_step", "migrated", "n_total" (owned + halo particles held), "lean_steps" / "lean_pauses"
+ * (steps replayed with the lean sequence / of which had to be finished with the full one) */
 int sphb200_get_stat(sphb200_sim *sim, const char *name, double *value);
 /* Device time (ms, CUDA events) of the stages of ONE extra step — the reference's TimerOutputs
  * report (SimMetaData.HourGlass, labels "01" .. "12", src/SPHCellList.jl:748-800) with the labels
