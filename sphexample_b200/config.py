@@ -227,6 +227,7 @@ class SimulationMetaData:
     IndexCounter: int = 0
     TimeSteps: list = field(default_factory=list)
     ExportSingleVTKHDF: bool = True       # :49 one transient .vtkhdf file (True) or one file per output (False)
+    ExportGridCells: bool = False         # :50 also write the occupied cells as an UnstructuredGrid file
     OutputVariables: Optional[Sequence[str]] = None    # :51-65; None = the reference's default list
 
     def __post_init__(self):

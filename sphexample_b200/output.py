@@ -276,13 +276,16 @@ def vtk_point_data(state: dict, particles=None, variable_names=None):
     return names, [avail[v] for v in names]
 
 
-def SetupVTKOutput(save_location: str, simulation_name: str, export_single: bool = True, variable_names=None, particles=None):
-    """`SetupVTKOutput` (src/ProduceHDFVTK.jl:461-621) for particle files: returns (save_particles(iteration,
-    total_time, state), close_files()).  Multi-file mode writes `<name>_<iteration, 6 digits>.vtkhdf`, single-file
-    mode appends to `<name>.vtkhdf`."""
+def SetupVTKOutput(save_location: str, simulation_name: str, export_single: bool = True, variable_names=None, particles=None,
+                   export_grid_cells: bool = False, H: float = 0.0):
+    """`SetupVTKOutput` (src/ProduceHDFVTK.jl:461-621): returns (save_particles(iteration, total_time, state),
+    close_files()) — and, with `export_grid_cells` (SimMetaData.ExportGridCells; needs the cell edge H), a third
+    function save_grid(iteration, total_time, unique_cells).  Multi-file mode writes `<name>_<iteration, 6 digits>.vtkhdf`
+    (grid: `CellGrid_<name>_<iteration>.vtkhdf`), single-file mode appends to `<name>.vtkhdf` (`<name>_GridCells.vtkhdf`)."""
     import os
     base = os.path.join(save_location, simulation_name)
-    tr = {"w": None}
+    grid_base = os.path.join(save_location, "CellGrid_" + simulation_name)
+    tr = {"w": None, "g": None}
 
     def save_particles(iteration: int, total_time: float, state: dict):
         names, arrays = vtk_point_data(state, particles, variable_names)
@@ -292,10 +295,21 @@ def SetupVTKOutput(save_location: str, simulation_name: str, export_single: bool
             tr["w"] = VTKHDFTransient(base + ".vtkhdf", names, *arrays)
         tr["w"].append(total_time, state["Position"], *arrays)
 
-    def close_files():
-        if tr["w"] is not None:
-            tr["w"].close()
+    def save_grid(iteration: int, total_time: float, unique_cells):
+        if not export_single:
+            return SaveCellGridVTKHDF(f"{grid_base}_{int(iteration):06d}.vtkhdf", H, unique_cells)
+        if tr["g"] is None:
+            tr["g"] = VTKHDFGridTransient(base + "_GridCells.vtkhdf", H)
+        tr["g"].append(total_time, unique_cells)
 
+    def close_files():
+        for k in ("w", "g"):
+            if tr[k] is not None:
+                tr[k].close()
+
+    if export_grid_cells:
+        assert H > 0.0, "export_grid_cells needs the cell edge H"
+        return save_particles, close_files, save_grid
     return save_particles, close_files
 
 
@@ -352,3 +366,70 @@ def SaveCellGridVTKHDF(filepath: str, H: float, unique_cells: np.ndarray) -> int
     g.group("CellData").dataset("CellData", cell_data)
     g.group("FieldData")
     return h5.write_file(filepath, root)
+
+
+class VTKHDFGridTransient:
+    """The single-file cell-grid output (`GenerateGeometryStructure` / `GenerateStepStructure` with
+    vtk_file_type = "UnstructuredGrid" + `AppendVTKHDFGridData`, src/ProduceHDFVTK.jl:163-230,327-414): every
+    `append` adds the occupied cells of one output as quads / hexahedra.  As the reference writes it: connectivity
+    ids are local to the step (0 .. points-1), `Steps/ConnectivityIdOffsets` and `Steps/PointOffsets` both hold the
+    points written before the step, `Steps/CellOffsets` the cells written before it, `CellData/ChunkID` the ChunkID
+    column's first n_cells entries (0 here: ChunkID is a threading detail of the reference's loop)."""
+
+    def __init__(self, filepath: str, H: float):
+        from . import hdf5_min as h5
+        self._h5, self.filepath, self.H = h5, filepath, float(H)
+        self.points = h5.Spool(np.float64, (3,))
+        self.conn, self.offs, self.cdata, self.chunk = (h5.Spool(np.int64) for _ in range(4))
+        self.types = h5.Spool(np.uint8)
+        self.values, self.npoints, self.ncells = [], [], []
+        self.closed = False
+
+    def append(self, new_step: float, unique_cells: np.ndarray):
+        points, connectivity, offsets, cell_types, cell_data = compute_grid_geometry(self.H, unique_cells)
+        self.points.append(points)
+        self.conn.append(connectivity)
+        self.offs.append(offsets)
+        self.types.append(cell_types)
+        self.cdata.append(cell_data)
+        self.chunk.append(np.zeros(len(cell_data), np.int64))
+        self.values.append(float(new_step))
+        self.npoints.append(int(points.shape[0]))
+        self.ncells.append(int(cell_types.shape[0]))
+
+    def close(self) -> int:
+        if self.closed:
+            return 0
+        h5 = self._h5
+        ns = len(self.values)
+        npts, ncel = np.asarray(self.npoints, np.int64), np.asarray(self.ncells, np.int64)
+        before = lambda a: (np.concatenate([[0], np.cumsum(a)[:-1]]).astype(np.int64) if ns else np.zeros(0, np.int64))
+        root = h5.Group()
+        g = root.group("VTKHDF")
+        g.attrs["Version"] = np.array([2, 3], np.int32)
+        g.attrs["Type"] = b"UnstructuredGrid"
+        g.dataset("NumberOfPoints", npts)
+        g.dataset("Points", self.points)
+        g.dataset("Connectivity", self.conn)
+        g.dataset("NumberOfCells", ncel)
+        g.dataset("NumberOfConnectivityIds", npts)
+        g.dataset("Offsets", self.offs)
+        g.dataset("Types", self.types)
+        g.group("FieldData")
+        cd = g.group("CellData")
+        cd.dataset("CellData", self.cdata)
+        cd.dataset("ChunkID", self.chunk)
+        st = g.group("Steps")
+        st.attrs["NSteps"] = np.int32(ns)
+        st.dataset("Values", np.asarray(self.values, np.float64))
+        st.dataset("PartOffsets", np.arange(ns, dtype=np.int64))
+        st.dataset("NumberOfParts", np.ones(ns, np.int64))
+        st.dataset("PointOffsets", before(npts))
+        st.dataset("CellOffsets", before(ncel))
+        st.dataset("ConnectivityIdOffsets", before(npts))
+        st.group("PointDataOffsets")
+        size = h5.write_file(self.filepath, root)
+        for sp in (self.points, self.conn, self.offs, self.cdata, self.chunk, self.types):
+            sp.close()
+        self.closed = True
+        return size

@@ -275,10 +275,20 @@ def RunSimulation(*, SimGeometry=(), SimMetaData, SimConstants, SimKernel, SimPa
         # the initial state first, with OutputIterationCounter = 1
         from . import output as _out
         os.makedirs(meta.SaveLocation, exist_ok=True)
-        save_vtk, close_files = _out.SetupVTKOutput(meta.SaveLocation, meta.SimulationName or "Simulation",
-                                                    export_single=bool(getattr(meta, "ExportSingleVTKHDF", True)),
-                                                    variable_names=getattr(meta, "OutputVariables", None), particles=SimParticles)
-        save_particles = lambda counter, state, rep: save_vtk(counter, rep["total_time"] if rep else meta.TotalTime, state)
+        grid = bool(getattr(meta, "ExportGridCells", False))
+        fns = _out.SetupVTKOutput(meta.SaveLocation, meta.SimulationName or "Simulation",
+                                  export_single=bool(getattr(meta, "ExportSingleVTKHDF", True)),
+                                  variable_names=getattr(meta, "OutputVariables", None), particles=SimParticles,
+                                  export_grid_cells=grid, H=float(SimKernel.H))
+        save_vtk, close_files = fns[0], fns[1]
+
+        def save_particles(counter, state, rep):
+            t = rep["total_time"] if rep else meta.TotalTime
+            save_vtk(counter, t, state)
+            if grid:                                               # output.save_grid(...), :850,891
+                if rep is None:
+                    sim.UpdateNeighbors()                          # the reference builds the cell list before the first output (:838-843)
+                fns[2](counter, t, sim.cell_list()[0])
         meta.OutputIterationCounter = 1
         save_particles(1, sim.download(), None)
     try:

@@ -224,3 +224,44 @@ def test_cell_grid_file_has_the_reference_layout(tmp_path, dim):
         b = pts[which[tuple(cc[j])]]
         x = case.particles.Position[j].astype(np.float64)
         assert np.all(x >= b.min(axis=0)[:dim] - 1e-9) and np.all(x <= b.max(axis=0)[:dim] + 1e-9)
+
+
+def test_transient_cell_grid_file_appends_steps_like_the_reference(tmp_path):
+    """AppendVTKHDFGridData (src/ProduceHDFVTK.jl:327-414): per step the occupied cells' corners, step-local
+    connectivity, and offsets of points / cells written before the step"""
+    from sphexample_b200.slab import cell_coord
+    case = util.case_c1("float64")
+    H = 1.0 / util.params_of(case).H_inv
+    steps = []
+    for k in range(3):
+        x = case.particles.Position + 0.3 * k * H
+        steps.append(np.unique(np.stack([cell_coord(x[:, d], 1.0 / H) for d in range(2)], axis=1), axis=0)[: 200 + 17 * k])
+    save, close, save_grid = output.SetupVTKOutput(str(tmp_path), "Sim", export_single=True, variable_names=["Density"],
+                                                   export_grid_cells=True, H=H)
+    for k, cells in enumerate(steps):
+        save_grid(k + 1, 0.1 * k, cells)
+    close()
+    tree = h5_minread.Reader(str(tmp_path / "Sim_GridCells.vtkhdf")).tree()
+    nc = np.array([len(c) for c in steps])
+    a = tree["/VTKHDF@"]
+    assert a["Version"].dtype == np.int32 and bytes(a["Type"]) == b"UnstructuredGrid" and tree["/VTKHDF/Steps@"]["NSteps"] == 3
+    assert tree["/VTKHDF/NumberOfCells"].tolist() == nc.tolist() and tree["/VTKHDF/NumberOfPoints"].tolist() == (4 * nc).tolist()
+    assert tree["/VTKHDF/NumberOfConnectivityIds"].tolist() == (4 * nc).tolist()
+    assert tree["/VTKHDF/Steps/Values"].tolist() == [0.0, 0.1, 0.2]
+    assert tree["/VTKHDF/Steps/PointOffsets"].tolist() == [0, 4 * nc[0], 4 * (nc[0] + nc[1])]
+    assert tree["/VTKHDF/Steps/ConnectivityIdOffsets"].tolist() == tree["/VTKHDF/Steps/PointOffsets"].tolist()
+    assert tree["/VTKHDF/Steps/CellOffsets"].tolist() == [0, nc[0], nc[0] + nc[1]]
+    assert tree["/VTKHDF/Steps/PartOffsets"].tolist() == [0, 1, 2] and tree["/VTKHDF/Steps/NumberOfParts"].tolist() == [1, 1, 1]
+    assert tree["/VTKHDF/Points"].shape == (4 * nc.sum(), 3) and tree["/VTKHDF/Types"].tolist() == [9] * int(nc.sum())
+    assert tree["/VTKHDF/Offsets"].shape == (nc.sum() + 3,)                       # n_cells + 1 per step
+    conn = tree["/VTKHDF/Connectivity"]
+    assert np.array_equal(conn[4 * nc[0]:4 * (nc[0] + nc[1])], np.arange(4 * nc[1]))   # step-local ids
+    p1 = tree["/VTKHDF/Points"][4 * nc[0]:4 * (nc[0] + nc[1])].reshape(nc[1], 4, 3)
+    assert np.allclose(p1.mean(axis=1)[:, :2], steps[1] * H)
+    assert tree["/VTKHDF/CellData/CellData"].shape == (nc.sum(),) and not tree["/VTKHDF/CellData/ChunkID"].any()
+    # multi-file mode: one static grid file per output, named like the reference's
+    save, close, save_grid = output.SetupVTKOutput(str(tmp_path), "Multi", export_single=False, export_grid_cells=True, H=H)
+    save_grid(7, 0.7, steps[0])
+    close()
+    t7 = h5_minread.Reader(str(tmp_path / "CellGrid_Multi_000007.vtkhdf")).tree()
+    assert t7["/VTKHDF/NumberOfCells"].tolist() == [nc[0]]
