@@ -248,6 +248,27 @@ SPH_HD void step_end(Ctl *ctl) {
     ctl->vbox_cur ^= 1;   // k_cell_vbox of the next step head writes the other buffer
 }
 
+// Host side of the lean step sequence: how many of the next steps can be enqueued without the UpdateNeighbors!
+// chain (and, with lists, without the cull kernels), judged from the host's copy of the control block after a
+// synchronisation.  delta_x grows by about last_disp4 per step and triggers at h (step_control); the estimate
+// keeps a 10 % + one step margin — a miss is not an error (the step pauses itself), only a wasted batch tail.
+// 0 = take a full step next.  list_skin = skin in length units (0: no lists), batch = the most the caller enqueues.
+SPH_HD long long lean_steps_ahead(const Ctl &c, double h, double list_skin, long long batch) {
+    if (!c.red_ready || c.done || c.error) return 0;
+    if (list_skin > 0.0) {
+        // while the lists are off (after an overflow) or the half-step displacement is about to outgrow the skin
+        // (pass 2 falls back to the cull kernel: list_mode[1] in step_control), full steps
+        if (c.list_off || c.list_fail || !c.list_valid) return 0;
+        if (c.dt2 * c.vmax_now > 0.9 * 0.49 * list_skin) return 0;
+    }
+    const double room = h - c.delta_x;
+    if (!(room > 0.0)) return 0;
+    const double d = c.last_disp4;
+    if (!(d > 0.0)) return batch;
+    const double k = 0.9 * room / d - 1.0;
+    return k < 1.0 ? 0 : (long long)(k < (double)batch ? k : (double)batch);
+}
+
 // Per-brick list validity.  A pair (a, b) of a brick's window that is NOT in a's list was farther
 // apart than H + skin when the list was built; it is missed only if the two have approached by more
 // than skin since.  Over one step the relative displacement of a and b is

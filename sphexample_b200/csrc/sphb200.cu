@@ -1348,19 +1348,8 @@ class Sim final : public sphb200_sim {
     // how many of the next steps can go without UpdateNeighbors!, from the host's copy of the control block:
     // delta_x grows by about last_disp4 per step and triggers at h (step_control); 0 = the next step rebuilds
     int64_t lean_steps_ahead() const {
-        if (!opt_lean || !have_cells || !have_half || !h_ctl->red_ready || h_ctl->done || h_ctl->error) return 0;
-        if (lists_on()) {
-            // the lean sequence has no cull kernels: while the lists are off (after an overflow) or the half-step
-            // displacement is about to outgrow the skin (pass 2 falls back to the cull kernel), take full steps
-            if (h_ctl->list_off || h_ctl->list_fail || !h_ctl->list_valid) return 0;
-            if (h_ctl->dt2 * h_ctl->vmax_now > 0.9 * 0.49 * opt_skin * prm.H) return 0;
-        }
-        const double room = (double)ph.h - h_ctl->delta_x;
-        if (!(room > 0.0)) return 0;
-        const double d = h_ctl->last_disp4;
-        if (!(d > 0.0)) return opt_batch;
-        const double k = 0.9 * room / d - 1.0;
-        return k < 1.0 ? 0 : (int64_t)std::min<double>(k, (double)opt_batch);
+        if (!opt_lean || !have_cells || !have_half) return 0;
+        return sph::lean_steps_ahead(*h_ctl, (double)ph.h, lists_on() ? opt_skin * prm.H : 0.0, opt_batch);
     }
 
     int run_steps(int64_t nsteps, bool until_target) {

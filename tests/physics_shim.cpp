@@ -207,6 +207,10 @@ extern "C" void shim_ctl_head(void *p, double disp2, double visc, double acc2, d
     out[0] = s->ctl.dt; out[1] = s->ctl.do_rebuild; out[2] = s->ctl.list_build; out[3] = s->ctl.list_mode[0];
     out[4] = s->ctl.list_mode[1]; out[5] = s->ctl.done; out[6] = s->ctl.list_move; out[7] = s->ctl.delta_x;
 }
+extern "C" long long shim_ctl_lean_ahead(void *p, double h, double skin, long long batch) {
+    return lean_steps_ahead(((ShimCtl *)p)->ctl, h, skin, batch);
+}
+extern "C" int shim_ctl_paused(void *p) { return ((ShimCtl *)p)->ctl.paused; }
 extern "C" void shim_ctl_body(void *p) {
     ShimCtl *s = (ShimCtl *)p;
     if (s->ctl.done && s->ctl.paused) { s->ctl.done = 0; s->ctl.paused = 0; }

@@ -230,3 +230,87 @@ def test_brick_bound_holds_for_relative_motion(shim):  # noqa: F811
         x = x + (v + v_new) / 2 * dt
         v_prev, v, dt_prev = v, v_new, dt
     assert builds >= 3 and global_builds > 4 * builds, (builds, global_builds)
+
+
+def test_lean_batches_predicted_from_the_control_block(shim):  # noqa: F811
+    """the host loop of run_steps (sphb200.cu) replayed on the CPU with the product's own step_control /
+    lean_steps_ahead: lean batches sized from the control block, a full step when the estimate says the next
+    step rebuilds, pause + resume when a lean step rebuilds after all.  With a steady flow the estimate never
+    misses; with an accelerating one a miss costs a pause, never a wrong decision."""
+    import ctypes as C
+    shim.shim_ctl_new.restype = C.c_void_p
+    shim.shim_ctl_new.argtypes = [C.c_double]
+    shim.shim_ctl_head.argtypes = [C.c_void_p] + [C.c_double] * 9 + [C.c_int, C.c_void_p]
+    shim.shim_ctl_body.argtypes = [C.c_void_p]
+    shim.shim_ctl_free.argtypes = [C.c_void_p]
+    shim.shim_ctl_lean_ahead.restype = C.c_longlong
+    shim.shim_ctl_lean_ahead.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_longlong]
+    shim.shim_ctl_paused.argtypes = [C.c_void_p]
+    h = H / 2.0
+    out = np.zeros(8)
+
+    def run(disp_of_step, nsteps, batch):
+        ctl = shim.shim_ctl_new(1.0 + h)
+        stats = {"lean": 0, "full": 0, "pauses": 0, "rebuilds": 0, "wasted": 0}
+        trace = []
+
+        def head(step, pause):
+            d = disp_of_step(step)
+            shim.shim_ctl_head(ctl, d * d, 0.0, 1.0, 0.0, h, C0, CFL, 0.0, 0.0, pause, out.ctypes.data)
+            return int(out[1]), int(out[5])
+        try:
+            step = 0
+            while step < nsteps:
+                ahead = shim.shim_ctl_lean_ahead(ctl, h, 0.0, batch)
+                if ahead >= 1:
+                    n = min(ahead, nsteps - step)
+                    for k in range(n):                       # the batch, enqueued blind
+                        rebuild, done = head(step, 1)
+                        if done:                             # paused: the rest of the batch runs empty
+                            assert rebuild == 1 and shim.shim_ctl_paused(ctl) == 1
+                            stats["pauses"] += 1
+                            stats["wasted"] += n - k - 1
+                            shim.shim_ctl_body(ctl)          # host: resume, full body with UpdateNeighbors!
+                            stats["rebuilds"] += 1
+                            trace.append(step)
+                            step += 1
+                            break
+                        shim.shim_ctl_body(ctl)
+                        stats["lean"] += 1
+                        step += 1
+                else:
+                    rebuild, done = head(step, 0)            # a full step: may rebuild in place
+                    assert not done
+                    shim.shim_ctl_body(ctl)
+                    stats["full"] += 1
+                    stats["rebuilds"] += rebuild
+                    if rebuild:
+                        trace.append(step)
+                    step += 1
+        finally:
+            shim.shim_ctl_free(ctl)
+        return stats, trace
+
+    def reference_rebuild_steps(disp_of_step, nsteps):      # the plain sequence: every step a full step
+        ctl = shim.shim_ctl_new(1.0 + h)
+        steps = []
+        for s in range(nsteps):
+            d = disp_of_step(s)
+            shim.shim_ctl_head(ctl, d * d, 0.0, 1.0, 0.0, h, C0, CFL, 0.0, 0.0, 0, out.ctypes.data)
+            if int(out[1]):
+                steps.append(s)
+            shim.shim_ctl_body(ctl)
+        shim.shim_ctl_free(ctl)
+        return steps
+
+    steady = lambda s: 0.006 * h                             # 4 * disp = 0.024 h per step: a rebuild every ~42 steps
+    st, tr = run(steady, 600, 64)
+    assert tr == reference_rebuild_steps(steady, 600) and len(tr) >= 10
+    assert st["pauses"] == 0 and st["lean"] >= 0.85 * 600 and st["full"] <= 8 * len(tr)
+    speeding = lambda s: 0.002 * h * (1.0 + 0.02 * s)        # the flow accelerates: the last increment underestimates the next ones
+    st, tr = run(speeding, 600, 64)
+    assert tr == reference_rebuild_steps(speeding, 600) and len(tr) >= 10
+    assert st["lean"] >= 0.75 * 600 and st["pauses"] <= len(tr) and st["wasted"] <= 3 * len(tr)
+    bursts = lambda s: (0.05 if s % 37 == 36 else 0.001) * h  # a sudden jump the estimate cannot see: the pause catches it
+    st, tr = run(bursts, 400, 64)
+    assert tr == reference_rebuild_steps(bursts, 400) and st["pauses"] >= 1
