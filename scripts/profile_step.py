@@ -3,7 +3,8 @@
 env: SPH_PREP=<seconds>  run the dam break that long first (the developed flow bench.py times) and
      switch the profiler on only afterwards (use `ncu --profile-from-start off`);
      SPH_VEL=<m/s>       (without SPH_PREP) a smooth velocity field as a cheap developed-flow proxy;
-     SPH_OPTS='k=v,k=v'  library options."""
+     SPH_OPTS='k=v,k=v'  library options;
+     SPH_RESET=1         re-arm the forced rebuild for the profiled steps."""
 import os
 import sys
 
@@ -39,7 +40,7 @@ if prep > 0:
 sim.step(3, reset_delta_x=True)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
-sim.step(steps)
+sim.step(steps, reset_delta_x=bool(os.environ.get("SPH_RESET")))   # SPH_RESET=1: the forced UpdateNeighbors! + full list build is in the profiled region
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
 print("ok", len(case.particles), dp, sim.report(), "list_wavefronts", sim.stat("list_wavefronts"), "list_entries", sim.stat("list_entries"))
