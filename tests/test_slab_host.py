@@ -151,3 +151,47 @@ def test_ghost_node_table_is_the_nonzero_ghost_rows_by_ascending_id():
     assert np.all(np.diff(gid) > 0) and np.array_equal(gid, np.sort(p.ID[has]))
     o = np.argsort(p.ID[has], kind="stable")
     assert np.array_equal(gp, p.GhostPoints[has][o])
+
+
+def _mdbc_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sphexample_b200 import simulation
+        simulation.comm_unique_id = lambda: bytes(range(128)) if rank == 0 else b"\xff" * 128
+        case = util.case_c5("float64")
+        p = util.params_of(case)
+
+        class Sim(_FakeSim):
+            params = p
+
+            def set_ghost_nodes(self, gp, ids):
+                self.calls.append(("set_ghost_nodes", np.asarray(gp).tobytes(), np.asarray(ids).tobytes(), len(ids)))
+        sim = Sim()
+        dec = slab.SlabDecomposition(sim, case.particles, p.H_inv, rank, world, axis=0).setup()
+        names = [c[0] for c in sim.calls]
+        own_ghosts = int(np.any(sim.uploaded.GhostPoints != 0, axis=1).sum())
+        q.put((rank, names, sim.calls[names.index("set_ghost_nodes")][1:], dec.n_owned, own_ghosts))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_every_rank_hands_over_the_same_ghost_node_table_with_gloo():
+    """slab-mode SimpleMDBC: comm_init, set_slab, then the WHOLE ghost-node table on every rank (not just the nodes of
+    the rank's own particles), then the rank's share of the particles"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_mdbc_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, names0, tab0, n0, g0), (r1, names1, tab1, n1, g1) = res
+    assert names0 == names1 == ["comm_init", "set_slab", "set_ghost_nodes"]
+    assert tab0 == tab1 and tab0[2] > 500                      # identical bytes on both ranks
+    assert n0 + n1 == 3027 and g0 + g1 == tab0[2] and 0 < g0 < tab0[2]   # each rank owns only a part of the nodes' particles

@@ -265,3 +265,67 @@ def test_transient_cell_grid_file_appends_steps_like_the_reference(tmp_path):
     close()
     t7 = h5_minread.Reader(str(tmp_path / "CellGrid_Multi_000007.vtkhdf")).tree()
     assert t7["/VTKHDF/NumberOfCells"].tolist() == [nc[0]]
+
+
+def test_random_trees_round_trip(tmp_path):
+    """property test of the HDF5 writer: random group trees (depth <= 3, up to 20 links per group, every supported
+    dtype, 0-d to 3-d shapes incl. empty ones, attributes) come back identical through the independent reader"""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    dtypes = [np.int8, np.uint8, np.int16, np.uint16, np.int32, np.uint32, np.int64, np.uint64, np.float32, np.float64]
+    names = st.text(alphabet="abcdefghijklmnopqrstuvwxyzABCDEFXYZ_0123456789", min_size=1, max_size=12)
+    shapes = st.lists(st.integers(0, 5), min_size=1, max_size=3).map(tuple)
+
+    @st.composite
+    def arrays(draw):
+        dt = draw(st.sampled_from(dtypes))
+        shp = draw(shapes)
+        n = int(np.prod(shp))
+        seed = draw(st.integers(0, 2 ** 31 - 1))
+        a = np.random.default_rng(seed).integers(-100, 100, n).astype(dt).reshape(shp)
+        return a
+
+    @st.composite
+    def groups(draw, depth=0):
+        g = {"attrs": draw(st.dictionaries(names, st.one_of(arrays(), st.binary(min_size=1, max_size=9).filter(lambda b: b"\0" not in b)),
+                                           max_size=3)), "kids": {}}
+        for nm in draw(st.lists(names, max_size=20 if depth == 0 else 6, unique=True)):
+            if depth < 2 and draw(st.integers(0, 4)) == 0:
+                g["kids"][nm] = draw(groups(depth + 1))
+            else:
+                g["kids"][nm] = draw(arrays())
+        return g
+
+    def build(spec, node, prefix, want):
+        for k, v in spec["attrs"].items():
+            node.attrs[k] = v
+            want.setdefault(prefix + "@", {})[k] = v
+        for nm, v in spec["kids"].items():
+            if isinstance(v, dict):
+                build(v, node.group(nm), prefix + "/" + nm, want)
+            else:
+                node.dataset(nm, v)
+                want[prefix + "/" + nm] = v
+
+    counter = [0]
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(groups())
+    def check(spec):
+        root, want = hdf5_min.Group(), {}
+        build(spec, root, "", want)
+        counter[0] += 1
+        path = str(tmp_path / f"r{counter[0]}.h5")
+        hdf5_min.write_file(path, root)
+        got = h5_minread.Reader(path).tree()
+        assert set(got) == set(want)
+        for k, v in want.items():
+            if k.endswith("@"):
+                assert set(got[k]) == set(v)
+                for an, av in v.items():
+                    if isinstance(av, bytes):
+                        assert bytes(got[k][an]) == av
+                    else:
+                        assert got[k][an].dtype == av.dtype and np.array_equal(got[k][an], av)
+            else:
+                assert got[k].dtype == v.dtype and got[k].shape == v.shape and np.array_equal(got[k], v)
+    check()
